@@ -1,0 +1,253 @@
+// C-ABI entry points of the binary QC-LDPC decode path (include/ldpc_b200.h).
+// ldpc_decode_batch replaces LDPC_Decoder_GPU (B/LDPC_Decoder.cuh:5, B/LDPC_Decoder.cu:23-164):
+// same inputs (channel values, frames interleaved [N][F]) and the same output array
+// D[(N+1)][F], but scratch is owned by the code handle instead of cudaMalloc/cudaFree per call
+// (:38-88, :160-163), nothing is copied to the host per iteration (:135) and errors are
+// returned, not printed.
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.h"
+
+namespace ldpcb {
+
+static std::mutex g_dev_mu;
+
+static int ensure_device(const ldpc_code *cc)
+{
+    ldpc_code *c = const_cast<ldpc_code *>(cc);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (c->device >= 0) return LDPC_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return LDPC_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0, sms = 0;
+    LDPC_CUDA_TRY(cudaGetDevice(&dev));
+    LDPC_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    LDPC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) return LDPC_ERR_NO_DEVICE;  // the library carries sm_100a code only
+    c->device = dev;
+    c->num_sms = sms;
+    return LDPC_OK;
+}
+
+// any dtype/layout -> fp32 [N][F]
+__global__ void __launch_bounds__(256)
+to_f32_nf_kernel(const void *__restrict__ in, float *__restrict__ out, int dtype, int layout, int N, int F)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)N * F) return;
+    const int n = (int)(tid / F), f = (int)(tid % F);
+    const size_t o = (layout == LDPC_LAYOUT_NF) ? (size_t)tid : (size_t)f * N + n;
+    float v;
+    if (dtype == LDPC_DTYPE_FP32)
+        v = reinterpret_cast<const float *>(in)[o];
+    else if (dtype == LDPC_DTYPE_FP16)
+        v = __half2float(reinterpret_cast<const __half *>(in)[o]);
+    else
+        v = (float)reinterpret_cast<const signed char *>(in)[o];
+    out[tid] = v;
+}
+
+// hard[N][F] (+ ok[F]) -> requested output format
+__global__ void __launch_bounds__(256)
+emit_hard_kernel(const unsigned char *__restrict__ hard, const int *__restrict__ ok, void *__restrict__ out,
+                 int out_format, int layout, int N, int F)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (out_format == LDPC_OUT_BITPACK) {
+        const int W = (N + 31) / 32;
+        if (tid >= (long long)W * F) return;
+        const int f = (int)(tid % F), w = (int)(tid / F);
+        unsigned bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const int n = w * 32 + b;
+            if (n < N && hard[(size_t)n * F + f]) bits |= 1u << b;
+        }
+        reinterpret_cast<unsigned *>(out)[(size_t)f * W + w] = bits;
+        return;
+    }
+    if (tid >= (long long)(N + 1) * F) return;
+    const int n = (int)(tid / F), f = (int)(tid % F);
+    if (out_format == LDPC_OUT_INT32_REF) {
+        reinterpret_cast<int *>(out)[tid] = (n < N) ? (int)hard[tid] : ok[f];
+    } else if (n < N) {
+        const size_t o = (layout == LDPC_LAYOUT_NF) ? (size_t)tid : (size_t)f * N + n;
+        reinterpret_cast<unsigned char *>(out)[o] = hard[tid];
+    }
+}
+
+static size_t dtype_bytes(int dt) { return dt == LDPC_DTYPE_FP32 ? 4 : (dt == LDPC_DTYPE_FP16 ? 2 : 1); }
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace ldpcb
+
+using namespace ldpcb;
+
+extern "C" void ldpc_decode_opts_default(ldpc_decode_opts_t *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->struct_size = (int)sizeof(*o);
+    o->batch = 0;
+    o->layout = LDPC_LAYOUT_NF;
+    o->llr_dtype = LDPC_DTYPE_FP32;
+    o->mem_space = LDPC_MEM_HOST;
+    o->schedule = LDPC_SCHED_FLOODING;  // the reference's schedule and arithmetic
+    o->msg_dtype = LDPC_DTYPE_FP32;
+    o->early_exit = LDPC_EXIT_NONE;
+    o->out_format = LDPC_OUT_INT32_REF;
+    o->alpha = 1.0f;
+    o->llr_scale = 8.0f;
+    o->msg_max = 127;
+    o->beta_num = 0;
+    o->beta_shift = 0;
+}
+
+extern "C" size_t ldpc_out_bytes(const ldpc_code_t *c, int F, int fmt)
+{
+    if (!c || F <= 0) return 0;
+    switch (fmt) {
+        case LDPC_OUT_INT32_REF: return (size_t)(c->N + 1) * F * sizeof(int);
+        case LDPC_OUT_U8: return (size_t)c->N * F;
+        case LDPC_OUT_BITPACK: return (size_t)((c->N + 31) / 32) * F * sizeof(unsigned);
+        default: return 0;
+    }
+}
+
+extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *hard_bits, int iters,
+                                 const ldpc_decode_opts_t *o)
+{
+    if (!c || !llr || !hard_bits || !o || iters <= 0) return LDPC_ERR_ARG;
+    if (o->struct_size != (int)sizeof(ldpc_decode_opts_t)) return LDPC_ERR_ARG;
+    const int F = o->batch;
+    if (F <= 0) return LDPC_ERR_ARG;
+    if (o->layout != LDPC_LAYOUT_NF && o->layout != LDPC_LAYOUT_FN) return LDPC_ERR_ARG;
+    if (o->llr_dtype < 0 || o->llr_dtype > 2 || o->out_format < 0 || o->out_format > 2) return LDPC_ERR_ARG;
+    if (o->early_exit < 0 || o->early_exit > 2) return LDPC_ERR_ARG;
+    const bool flooding = (o->schedule == LDPC_SCHED_FLOODING);
+    if (!flooding && o->schedule != LDPC_SCHED_LAYERED) return LDPC_ERR_ARG;
+    if (flooding && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
+    if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8 && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
+    if (!flooding && o->early_exit == LDPC_EXIT_GENIE) return LDPC_ERR_UNSUPPORTED;
+    int rc = ensure_device(c);
+    if (rc != LDPC_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
+    const bool host = (o->mem_space == LDPC_MEM_HOST);
+    const size_t in_bytes = (size_t)c->N * F * dtype_bytes(o->llr_dtype);
+    const size_t out_bytes = ldpc_out_bytes(c, F, o->out_format);
+    const size_t dbg_app_bytes = o->debug_app ? (size_t)c->N * F * (flooding ? 0 : (o->msg_dtype == LDPC_DTYPE_INT8 ? 1 : 4)) : 0;
+    const size_t dbg_msg_bytes =
+        o->debug_msgs ? (flooding ? (size_t)c->M * c->dc_max * F * 4 : (size_t)c->M * 4 * F * 4) : 0;
+
+    // ---- scratch carve-up (one arena per handle; decode calls on one handle serialise on it)
+    size_t need = 0;
+    const size_t o_in = need;      need += host ? align_up(in_bytes) : 0;
+    const size_t o_out = need;     need += host ? align_up(out_bytes) : 0;
+    const size_t o_it = need;      need += align_up((size_t)F * 4);
+    const size_t o_ok = need;      need += align_up((size_t)F * 4);
+    const size_t o_dapp = need;    need += host ? align_up(dbg_app_bytes) : 0;
+    const size_t o_dmsg = need;    need += (host && !flooding) ? align_up(dbg_msg_bytes) : 0;
+    size_t o_y = 0, o_msgs = 0, o_hard = 0, o_flags = 0;
+    const bool need_conv = flooding && (o->llr_dtype != LDPC_DTYPE_FP32 || o->layout != LDPC_LAYOUT_NF);
+    if (flooding) {
+        o_y = need;     need += need_conv ? align_up((size_t)c->N * F * 4) : 0;
+        o_msgs = need;  need += align_up((size_t)c->M * c->dc_max * F * 4);
+        o_hard = need;  need += align_up((size_t)c->N * F);
+        o_flags = need; need += align_up((size_t)(2 * F + 1) * 4);
+    }
+    const size_t o_layer = need;  // the layered kernel sizes its own slice behind this offset
+    unsigned char *base = nullptr;
+    size_t layered_extra = 0;
+    if (!flooding && o->msg_dtype == LDPC_DTYPE_INT8) {
+        rc = layered_i8_scratch_bytes(c, F, o->beta_num, &layered_extra);
+        if (rc != LDPC_OK) return rc;
+    }
+    rc = ensure_scratch(c, need + layered_extra, reinterpret_cast<void **>(&base));
+    if (rc != LDPC_OK) return rc;
+
+    const void *d_in = llr;
+    void *d_out = hard_bits;
+    int *d_it = o->iters_out, *d_ok = o->ok_out;
+    void *d_dapp = o->debug_app, *d_dmsg = o->debug_msgs;
+    if (host) {
+        d_in = base + o_in;
+        d_out = base + o_out;
+        LDPC_CUDA_TRY(cudaMemcpyAsync(base + o_in, llr, in_bytes, cudaMemcpyHostToDevice, st));
+        d_it = reinterpret_cast<int *>(base + o_it);
+        d_ok = reinterpret_cast<int *>(base + o_ok);
+        if (o->debug_app) d_dapp = base + o_dapp;
+        if (o->debug_msgs) d_dmsg = base + o_dmsg;
+    } else {
+        if (!d_it) d_it = reinterpret_cast<int *>(base + o_it);
+        if (!d_ok) d_ok = reinterpret_cast<int *>(base + o_ok);
+    }
+    int launches = 0;
+    if (flooding) {
+        const float *y = reinterpret_cast<const float *>(d_in);
+        if (need_conv) {
+            float *yc = reinterpret_cast<float *>(base + o_y);
+            const long long n = (long long)c->N * F;
+            to_f32_nf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, yc, o->llr_dtype, o->layout, c->N, F);
+            launches++;
+            y = yc;
+        }
+        float *msgs = reinterpret_cast<float *>(base + o_msgs);
+        unsigned char *hard = base + o_hard;
+        rc = launch_flooding_fp32(c, y, F, iters, o->early_exit, hard, d_it, d_ok, msgs,
+                                  reinterpret_cast<int *>(base + o_flags), st, &launches);
+        if (rc != LDPC_OK) return rc;
+        const long long n = (o->out_format == LDPC_OUT_BITPACK) ? (long long)((c->N + 31) / 32) * F
+                                                                : (long long)(c->N + 1) * F;
+        emit_hard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hard, d_ok, d_out, o->out_format, o->layout,
+                                                                    c->N, F);
+        launches++;
+        LDPC_CUDA_TRY(cudaGetLastError());
+        if (o->debug_msgs)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_msgs, msgs, dbg_msg_bytes,
+                                          host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    } else {
+        LayeredArgs a;
+        a.llr = d_in;
+        a.llr_dtype = o->llr_dtype;
+        a.layout = o->layout;
+        a.F = F;
+        a.iters = iters;
+        a.exit_mode = o->early_exit;
+        a.out_format = o->out_format;
+        a.scale = o->llr_scale;
+        a.msg_max = o->msg_max;
+        a.beta_num = o->beta_num;
+        a.beta_shift = o->beta_shift;
+        a.alpha = o->alpha;
+        a.out = d_out;
+        a.iters_out = d_it;
+        a.ok_out = d_ok;
+        a.dbg_app = d_dapp;
+        a.dbg_rec = d_dmsg;
+        a.scratch = base + o_layer;
+        a.scratch_bytes = layered_extra;
+        if (o->msg_dtype == LDPC_DTYPE_INT8)
+            rc = launch_layered_i8(c, a, st, &launches);
+        else
+            rc = launch_layered_fp32(c, a, st, &launches);
+        if (rc != LDPC_OK) return rc;
+        if (host && o->debug_msgs)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_msgs, d_dmsg, dbg_msg_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (host) {
+        LDPC_CUDA_TRY(cudaMemcpyAsync(hard_bits, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        if (o->iters_out)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->iters_out, d_it, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+        if (o->ok_out) LDPC_CUDA_TRY(cudaMemcpyAsync(o->ok_out, d_ok, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+        if (o->debug_app && dbg_app_bytes)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_app, d_dapp, dbg_app_bytes, cudaMemcpyDeviceToHost, st));
+        LDPC_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return launches;
+}

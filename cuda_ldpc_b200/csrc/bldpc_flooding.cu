@@ -1,0 +1,251 @@
+// Flooding un-normalised min-sum, fp32 — the strict-parity mode.
+//
+// Same update rules, message memory layout and iteration structure as the reference
+// (B/LDPC_Decoder.cu:94-131 host loop, :172-261 VN kernels, :262-372 CN kernels), on the true
+// circulant graph.  Messages live in msgs[(m*dc_max + p)*F + f] exactly like Memory_RQ
+// (B/LDPC_Decoder.cu:38, slot = check*Wc_max + position), frames fastest, so every access of a
+// warp is a coalesced 128-bit load/store over 4 consecutive frames.  The circulant shift is
+// address arithmetic (no Address_Variablenode table in memory).  fp32 adds are issued in the
+// reference's order, so results are bit-identical to the oracle (oracle/bldpc_oracle.c).
+//
+// HBM bound: (4E + 2N) * 4 bytes per codeword-iteration (SURVEY §8d "reference layout").
+#include "common.h"
+
+namespace ldpcb {
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    using T = float4;
+};
+template <>
+struct Vec<1> {
+    using T = float;
+};
+
+__device__ __forceinline__ float vget(const float4 &v, int j) { return (&v.x)[j]; }
+__device__ __forceinline__ float vget(const float &v, int) { return v; }
+__device__ __forceinline__ void vset(float4 &v, int j, float x) { (&v.x)[j] = x; }
+__device__ __forceinline__ void vset(float &v, int, float x) { v = x; }
+
+// Variablenode_Kernel (B/LDPC_Decoder.cu:172-216): S = sum_i R_i + y; D = S < 0; Q_i = S - R_i.
+template <int VEC, int MAXDV>
+__global__ void __launch_bounds__(256)
+flood_vn_kernel(const __grid_constant__ ColumnTables ct, float *__restrict__ msgs, const float *__restrict__ y,
+                unsigned char *__restrict__ hard, const int *__restrict__ done, int N, int Z, int F, int dcmax)
+{
+    using V = typename Vec<VEC>::T;
+    const int FV = F / VEC;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)N * FV) return;
+    const int n = (int)(tid / FV);
+    const int f = (int)(tid % FV) * VEC;
+    const int c = n / Z, j = n - c * Z;
+    const int dv = ct.dv[c], voff = ct.voff[c];
+    V R[MAXDV];
+    size_t ad[MAXDV];
+#pragma unroll
+    for (int i = 0; i < MAXDV; i++) {
+        if (i < dv) {
+            const int e = voff + i;
+            int row = j - (int)ct.shift[e];
+            row += (row < 0) ? Z : 0;
+            ad[i] = ((size_t)((int)ct.row[e] * Z + row) * dcmax + ct.pos[e]) * F + f;
+            R[i] = *reinterpret_cast<const V *>(msgs + ad[i]);
+        }
+    }
+    const V yy = *reinterpret_cast<const V *>(y + (size_t)n * F + f);
+    V S;
+#pragma unroll
+    for (int l = 0; l < VEC; l++) {
+        float s = 0.0f;  // the reference leaves Add_result uninitialised; 0 is the intent
+#pragma unroll
+        for (int i = 0; i < MAXDV; i++)
+            if (i < dv) s = __fadd_rn(s, vget(R[i], l));
+        s = __fadd_rn(s, vget(yy, l));
+        vset(S, l, s);
+        if (!done || !done[f + l]) hard[(size_t)n * F + f + l] = (s < 0.0f) ? 1 : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXDV; i++) {
+        if (i < dv) {
+            V q;
+#pragma unroll
+            for (int l = 0; l < VEC; l++) vset(q, l, __fsub_rn(vget(S, l), vget(R[i], l)));
+            *reinterpret_cast<V *>(msgs + ad[i]) = q;
+        }
+    }
+}
+
+// Checknode_Kernel (B/LDPC_Decoder.cu:262-314) + sortQ (:374-398): two smallest magnitudes,
+// first index of the smallest, product of signs (zero counts as +), no scaling.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+flood_cn_kernel(const __grid_constant__ LayerTables lt, float *__restrict__ msgs, int M, int Z, int F, int dcmax)
+{
+    using V = typename Vec<VEC>::T;
+    const int FV = F / VEC;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)M * FV) return;
+    const int m = (int)(tid / FV);
+    const int f = (int)(tid % FV) * VEC;
+    const int dc = lt.dc[m / Z];
+    float *base = msgs + ((size_t)m * dcmax) * F + f;
+    float min1[VEC], min2[VEC];
+    int idx[VEC];
+    unsigned neg[VEC];
+#pragma unroll
+    for (int l = 0; l < VEC; l++) {
+        min1[l] = __int_as_float(0x7f800000);
+        min2[l] = __int_as_float(0x7f800000);
+        idx[l] = 0;
+        neg[l] = 0;
+    }
+    for (int i = 0; i < dc; i++) {
+        const V q = *reinterpret_cast<const V *>(base + (size_t)i * F);
+#pragma unroll
+        for (int l = 0; l < VEC; l++) {
+            const float v = vget(q, l);
+            const float a = (v < 0.0f) ? -v : v;
+            neg[l] |= (v < 0.0f ? 1u : 0u) << i;
+            if (a < min1[l]) {
+                min2[l] = min1[l];
+                min1[l] = a;
+                idx[l] = i;
+            } else if (a < min2[l])
+                min2[l] = a;
+        }
+    }
+    for (int i = 0; i < dc; i++) {
+        V r;
+#pragma unroll
+        for (int l = 0; l < VEC; l++) {
+            const int sign_all = (__popc(neg[l]) & 1) ? -1 : 1;
+            const int sign_i = ((neg[l] >> i) & 1u) ? -1 : 1;
+            const float mag = (i != idx[l]) ? min1[l] : min2[l];
+            vset(r, l, __fmul_rn((float)(sign_all * sign_i), mag));
+        }
+        *reinterpret_cast<V *>(base + (size_t)i * F) = r;
+    }
+}
+
+// bad[f] |= 1 if any check of frame f has odd parity on hard[N][F]
+__global__ void __launch_bounds__(256)
+syndrome_nf_kernel(const __grid_constant__ LayerTables lt, const unsigned char *__restrict__ hard,
+                   int *__restrict__ bad, int M, int Z, int F)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)M * F) return;
+    const int m = (int)(tid / F), f = (int)(tid % F);
+    const int r = m / Z, i = m - r * Z;
+    const int dc = lt.dc[r], off = lt.off[r];
+    int p = 0;
+    for (int k = 0; k < dc; k++) {
+        int col = i + (int)lt.shift[off + k];
+        col -= (col >= Z) ? Z : 0;
+        p ^= hard[(size_t)((int)lt.col[off + k] * Z + col) * F + f];
+    }
+    if (p & 1) bad[f] = 1;
+}
+
+// genie test (B/LDPC_Decoder.cu:134-149): bad[f] = 1 if any of the first `length` bits is 1
+__global__ void __launch_bounds__(256)
+genie_nf_kernel(const unsigned char *__restrict__ hard, int *__restrict__ bad, int length, int F)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)length * F) return;
+    if (hard[tid]) bad[(int)(tid % F)] = 1;
+}
+
+// per-frame bookkeeping after iteration `it`; counter[0] += frames still running
+__global__ void __launch_bounds__(256)
+flood_finalize_kernel(const int *__restrict__ bad, int *__restrict__ done, int *__restrict__ iters,
+                      int *__restrict__ ok, int *__restrict__ counter, int it, int F, int latch)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    if (latch) {
+        if (done[f]) return;
+        iters[f] = it;
+        if (!bad[f]) {
+            done[f] = 1;
+            ok[f] = 1;
+        } else {
+            ok[f] = 0;
+            atomicAdd(counter, 1);
+        }
+    } else {
+        iters[f] = it;
+        ok[f] = bad[f] ? 0 : 1;
+        if (bad[f]) atomicAdd(counter, 1);
+    }
+}
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+template <int VEC>
+static void launch_vn(const ldpc_code *c, float *msgs, const float *y, unsigned char *hard, const int *done, int F,
+                      cudaStream_t st)
+{
+    const long long n = (long long)c->N * (F / VEC);
+    const unsigned g = blocks_for(n, 256);
+    if (c->dv_max <= 4)
+        flood_vn_kernel<VEC, 4><<<g, 256, 0, st>>>(c->ct, msgs, y, hard, done, c->N, c->Z, F, c->dc_max);
+    else if (c->dv_max <= 8)
+        flood_vn_kernel<VEC, 8><<<g, 256, 0, st>>>(c->ct, msgs, y, hard, done, c->N, c->Z, F, c->dc_max);
+    else
+        flood_vn_kernel<VEC, 16><<<g, 256, 0, st>>>(c->ct, msgs, y, hard, done, c->N, c->Z, F, c->dc_max);
+}
+
+// y_nf: device fp32 [N][F]; hard_nf: device u8 [N][F]; iters_dev/ok_dev: device int [F];
+// msgs: device fp32 [M*dc_max][F]; flag_scratch: device int [2F + 1] (bad, done, counter).
+int launch_flooding_fp32(const ldpc_code *c, const float *y, int F, int iters, int exit_mode,
+                         unsigned char *hard, int *iters_dev, int *ok_dev, float *msgs, int *flag_scratch,
+                         cudaStream_t st, int *launches)
+{
+    int *bad = flag_scratch, *done = flag_scratch + F, *counter = flag_scratch + 2 * F;
+    const size_t msg_bytes = (size_t)c->M * c->dc_max * F * sizeof(float);
+    LDPC_CUDA_TRY(cudaMemsetAsync(msgs, 0, msg_bytes, st));  // B/LDPC_Decoder.cu:82
+    LDPC_CUDA_TRY(cudaMemsetAsync(flag_scratch, 0, (size_t)(2 * F + 1) * sizeof(int), st));
+    const bool vec4 = (F % 4 == 0);
+    const int latch = (exit_mode == LDPC_EXIT_SYNDROME);
+    int n = 0, it = 0;
+    while (it < iters) {
+        it++;
+        if (vec4) {
+            launch_vn<4>(c, msgs, y, hard, latch ? done : nullptr, F, st);
+            flood_cn_kernel<4><<<blocks_for((long long)c->M * (F / 4), 256), 256, 0, st>>>(c->lt, msgs, c->M, c->Z,
+                                                                                          F, c->dc_max);
+        } else {
+            launch_vn<1>(c, msgs, y, hard, latch ? done : nullptr, F, st);
+            flood_cn_kernel<1><<<blocks_for((long long)c->M * F, 256), 256, 0, st>>>(c->lt, msgs, c->M, c->Z, F,
+                                                                                    c->dc_max);
+        }
+        n += 2;
+        const bool last = (it == iters);
+        if (exit_mode != LDPC_EXIT_NONE || last) {
+            LDPC_CUDA_TRY(cudaMemsetAsync(bad, 0, (size_t)F * sizeof(int), st));
+            LDPC_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), st));
+            if (exit_mode == LDPC_EXIT_GENIE)
+                genie_nf_kernel<<<blocks_for((long long)c->K * F, 256), 256, 0, st>>>(hard, bad, c->K, F);
+            else
+                syndrome_nf_kernel<<<blocks_for((long long)c->M * F, 256), 256, 0, st>>>(c->lt, hard, bad, c->M,
+                                                                                        c->Z, F);
+            flood_finalize_kernel<<<blocks_for(F, 256), 256, 0, st>>>(bad, done, iters_dev, ok_dev, counter, it, F,
+                                                                     latch);
+            n += 2;
+            if (exit_mode != LDPC_EXIT_NONE && !last) {
+                int running = 0;  // the reference copies N*F ints per iteration here (:135); we copy 4 bytes
+                LDPC_CUDA_TRY(cudaMemcpyAsync(&running, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+                LDPC_CUDA_TRY(cudaStreamSynchronize(st));
+                if (running == 0) break;
+            }
+        }
+    }
+    LDPC_CUDA_TRY(cudaGetLastError());
+    *launches += n;
+    return LDPC_OK;
+}
+
+}  // namespace ldpcb

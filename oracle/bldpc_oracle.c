@@ -19,7 +19,7 @@
  *     a_k    = min(|t_k|, amax)
  *     min1 <= min2 = two smallest a_k (with multiplicity), idx' = first k with a_k == min1
  *     P      = xor_k (t_k < 0)
- *     m1'    = (min1*anum) >> ashift,  m2' = (min2*anum) >> ashift
+ *     m1'    = min1 - ((min1*bnum) >> bshift),  m2' likewise   (bnum = 0: the reference's un-normalised rule)
  *     sign'_k= P ^ (t_k < 0);  new_k = (sign'_k ? -1 : +1) * (k == idx' ? m2' : m1')
  *     APP[v_k] = clamp(t_k + new_k, -127, 127)
  *   hard bit = APP < 0.  ORC_EXIT_SYNDROME tests H x = 0 after each full iteration.
@@ -362,7 +362,7 @@ int orc_layered_fp32(int J, int L, int Z, const int *H, const float *y, int F, i
 static inline int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int maxit,
-                   float scale, int amax, int anum, int ashift, int exit_mode, int *D,
+                   float scale, int amax, int bnum, int bshift, int exit_mode, int *D,
                    int *iters, int8_t *app_out, uint32_t *rec_out)
 {
     const int N = L * Z, M = J * Z;
@@ -402,7 +402,7 @@ int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int
                             min2 = ak;
                     }
                     if (min2 > amax) min2 = amax; /* dc == 1 only */
-                    const int m1 = (min1 * anum) >> ashift, m2 = (min2 * anum) >> ashift;
+                    const int m1 = min1 - ((min1 * bnum) >> bshift), m2 = min2 - ((min2 * bnum) >> bshift);
                     uint32_t sg = 0;
                     for (int k = 0; k < dc; k++) {
                         int s = P ^ neg[k];

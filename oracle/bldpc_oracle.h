@@ -68,7 +68,7 @@ int orc_layered_fp32(int J, int L, int Z, const int *H, const float *y, int F, i
  * y fp32 [N*F]; q = sat127(rint(y*scale)).  app_out (optional) int8 [N*F];
  * rec_out (optional) uint32 [M*4*F]: {m1, m2, idx, signs} per check per frame.     */
 int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int maxit,
-                   float scale, int amax, int anum, int ashift, int exit_mode, int *D,
+                   float scale, int amax, int bnum, int bshift, int exit_mode, int *D,
                    int *iters, int8_t *app_out, uint32_t *rec_out);
 
 /* true syndrome of hard bits x[N*F] (bit per int) -> ok[F] (1 = all checks satisfied) */

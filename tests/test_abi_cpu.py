@@ -1,0 +1,91 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/ldpc_b200.h declares,
+its loader agrees with the oracle's Get_H / Transform_H on all shipped H files, and decoding
+without a GPU fails loudly instead of falling back."""
+import ctypes as C
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT, OracleCode
+
+import cuda_ldpc_b200 as m
+
+BL = os.path.join(DATA, "bldpc")
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "ldpc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:nb_)?ldpc_[a-z0-9_]+|nb_decode_opts_default)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 20
+    L = C.CDLL(m.lib_path)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ldpc_b200.h but not exported"
+    assert b"sm_100a" in m.lib.ldpc_version()
+
+
+def geometry(path):
+    base = os.path.basename(path)
+    if base == "PON_LDPC.txt":
+        return 12, 69, 256
+    return tuple(int(x) for x in re.match(r"J(\d+)_L(\d+)_Z(\d+)", base).groups())
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(BL, "*.txt"))), ids=os.path.basename)
+def test_loader_matches_oracle_tables(oracle, path):
+    J, L, Z = geometry(path)
+    code = m.LdpcCode(path, *(geometry(path) if "PON" in path else (0, 0, 0)))
+    ref = OracleCode(oracle, path, J, L, Z, literal=0)
+    assert (code.J, code.L, code.Z, code.N, code.K, code.M) == (J, L, Z, L * Z, (L - J) * Z, J * Z)
+    H, Wc, Wv, addr = code.tables()
+    assert (H == ref.H).all() and (Wc == ref.Wc).all() and (Wv == ref.Wv).all()
+    assert (addr == ref.addr).all()
+    assert code.E == int((ref.H >= 0).sum()) * Z
+    assert code.dc_max == ref.Wc[J] and code.dv_max == ref.Wv[L]
+
+
+def test_loader_errors(tmp_path):
+    h = C.c_void_p()
+    assert m.lib.ldpc_load_code(b"/nonexistent/J4_L24_Z96_BlockH.txt", 0, 0, 0, C.byref(h)) == -1
+    assert m.lib.ldpc_load_code(os.path.join(BL, "PON_LDPC.txt").encode(), 0, 0, 0, C.byref(h)) == -3
+    # wrong geometry: too few / too many integers, shift >= Z
+    assert m.lib.ldpc_load_code(os.path.join(BL, "J4_L24_Z96_BlockH.txt").encode(), 5, 24, 96, C.byref(h)) == -2
+    assert m.lib.ldpc_load_code(os.path.join(BL, "J4_L24_Z96_BlockH.txt").encode(), 3, 24, 96, C.byref(h)) == -2
+    assert m.lib.ldpc_load_code(os.path.join(BL, "J4_L24_Z96_BlockH.txt").encode(), 4, 24, 64, C.byref(h)) == -2
+    # CRLF, tabs, leading blanks and no trailing newline parse like the reference's fscanf
+    p = tmp_path / "J2_L3_Z5_BlockH.txt"
+    p.write_bytes(b" 1\t-1\t 4\r\n\t0 2 -1")
+    c = m.LdpcCode(str(p))
+    assert c.tables()[0].tolist() == [1, -1, 4, 0, 2, -1] and (c.N, c.K, c.E) == (15, 5, 20)
+    assert m.lib.ldpc_strerror(-7).decode().startswith("no CUDA device")
+
+
+def test_decode_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    c = m.LdpcCode(os.path.join(BL, "J4_L24_Z96_BlockH.txt"))
+    with pytest.raises(m.LdpcError) as e:
+        c.decode(np.ones((c.N, 4), np.float32), 2)
+    assert e.value.code == -7
+
+
+def test_no_product_code_touches_the_oracle():
+    """The product path must never import, link or execute anything under oracle/."""
+    bad = []
+    for root, _, files in os.walk(os.path.join(ROOT, "cuda_ldpc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                txt = open(os.path.join(root, f), errors="replace").read()
+                # comments may cite the oracle as the specification; code may not use it
+                if re.search(r"liboracle|#\s*include\s*[<\"][^>\"]*oracle|^\s*(import|from)\s+\S*oracle|dlopen|"
+                             r"CDLL\([^)]*oracle", txt, flags=re.M):
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad

@@ -1,0 +1,182 @@
+"""GPU parity tests of the binary decode path, through the C-ABI (ctypes), against the CPU oracle
+and the golden vectors generated from the reference's own sources."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, GOLDEN, OracleCode, ip, fp
+
+import cuda_ldpc_b200 as m
+
+pytestmark = pytest.mark.gpu
+BL = os.path.join(DATA, "bldpc")
+
+CODES = {
+    "C1": ("J4_L24_Z96_BlockH.txt", 4, 24, 96),
+    "C2": ("J15_L30_Z1280_BlockH.txt", 15, 30, 1280),
+    "C3": ("PON_LDPC.txt", 12, 69, 256),
+    "J32": ("J32_L64_Z64_BlockH.txt", 32, 64, 64),
+    "J10": ("J10_L60_Z160_BlockH.txt", 10, 60, 160),
+    "J6": ("J6_L24_Z96_BlockH.txt", 6, 24, 96),
+}
+
+
+def load(oracle, key):
+    f, J, L, Z = CODES[key]
+    path = os.path.join(BL, f)
+    return m.LdpcCode(path, J, L, Z), OracleCode(oracle, path, J, L, Z, literal=0)
+
+
+def noisy(oracle, N, F, snr_db, seed=173, rate=1.0, snrtype=1):
+    s = np.array([seed, seed, seed], np.int32)
+    y = np.zeros(N * F, np.float32)
+    oracle.orc_awgn(ip(s), oracle.orc_sigma(snrtype, snr_db, rate), None, fp(y), N, F)
+    return y.reshape(N, F)
+
+
+def orc_flood(oracle, oc, y, maxit, mode):
+    N, F = y.shape
+    D = np.zeros((N + 1) * F, np.int32)
+    it = np.zeros(F, np.int32)
+    rq = np.zeros(oc.M * int(oc.Wc[oc.J]) * F, np.float32)
+    rc = oracle.orc_flooding_fp32(oc.J, oc.L, oc.Z, ip(oc.H), ip(oc.Wc), ip(oc.Wv), ip(oc.addr),
+                                  fp(np.ascontiguousarray(y)), F, maxit, mode, oc.K, ip(D), ip(it), rq.ctypes.data)
+    assert rc == 0
+    return D.reshape(N + 1, F), it, rq
+
+
+def orc_i8(oracle, oc, y, maxit, mode, scale=8.0, amax=127, bnum=0, bshift=0):
+    N, F = y.shape
+    D = np.zeros((N + 1) * F, np.int32)
+    it = np.zeros(F, np.int32)
+    app = np.zeros(N * F, np.int8)
+    rec = np.zeros(oc.M * 4 * F, np.uint32)
+    rc = oracle.orc_layered_i8(oc.J, oc.L, oc.Z, ip(oc.H), fp(np.ascontiguousarray(y)), F, maxit, scale, amax, bnum,
+                               bshift, mode, ip(D), ip(it), app.ctypes.data, rec.ctypes.data)
+    assert rc == 0
+    return D.reshape(N + 1, F), it, app.reshape(N, F), rec
+
+
+# ------------------------------------------------------------------ flooding fp32 (strict parity)
+
+def test_flooding_matches_reference_golden_batch(oracle):
+    """The reference's own LDPC_Decoder_GPU output (one-line-fixed Transform_H) on 16 frames."""
+    batch = np.load(os.path.join(GOLDEN, "binary_C1_batch16.npz"))
+    code, _ = load(oracle, "C1")
+    y = np.ascontiguousarray(batch["y"])
+    r = code.decode(y, 10, early_exit=m.EXIT_GENIE)
+    want = np.unpackbits(batch["D_fixed"], axis=0)[: code.N].astype(np.int32)
+    assert (r.D[: code.N] == want).all()
+    assert (r.D[code.N] == batch["flag_fixed"]).all()
+    assert (r.iters == int(batch["iters_fixed"])).all()
+    assert r.launches >= 20
+
+
+@pytest.mark.parametrize("key,F,snr", [("C1", 64, 3.0), ("C1", 37, 2.5), ("C3", 16, 3.5), ("C2", 8, -0.5),
+                                       ("J32", 24, 1.0), ("J10", 12, 4.0)])
+@pytest.mark.parametrize("mode", [m.EXIT_NONE, m.EXIT_GENIE, m.EXIT_SYNDROME])
+def test_flooding_bit_exact_vs_oracle(oracle, key, F, snr, mode):
+    code, oc = load(oracle, key)
+    y = noisy(oracle, code.N, F, snr)
+    r = code.decode(y, 10, early_exit=mode, debug=True)
+    D, it, rq = orc_flood(oracle, oc, y, 10, mode)
+    assert (r.D == D).all()
+    assert (r.iters == it).all()
+    if mode != m.EXIT_SYNDROME or it.max() == 10:
+        # every message, bit for bit (after an early syndrome exit the oracle stops at the same pass)
+        assert (r.msgs.view(np.uint32) == rq.view(np.uint32)).all()
+
+
+def test_flooding_input_variants(oracle):
+    """fp16 / int8 inputs and the [F][N] layout give the result of the converted fp32 [N][F] input."""
+    code, oc = load(oracle, "C1")
+    F = 20
+    y = noisy(oracle, code.N, F, 3.0)
+    y16 = y.astype(np.float16)
+    base = code.decode(y16.astype(np.float32), 8)
+    r16 = code.decode(y16, 8)
+    assert (r16.D == base.D).all()
+    rfn = code.decode(np.ascontiguousarray(y16.astype(np.float32).T), 8, layout=m.LAYOUT_FN, out_format=m.OUT_U8)
+    assert (rfn.D.T == base.D[: code.N]).all()
+    q = np.clip(np.rint(y * 8), -127, 127).astype(np.int8)
+    r8 = code.decode(q, 8, out_format=m.OUT_BITPACK)
+    b8 = code.decode(q.astype(np.float32), 8)
+    bits = ((r8.D[:, :, None] >> np.arange(32)[None, None, :]) & 1).reshape(F, -1)[:, : code.N]
+    assert (bits.T == b8.D[: code.N]).all()
+
+
+# ------------------------------------------------------------------ layered int8 (throughput mode)
+
+@pytest.mark.parametrize("key,F,snr,it", [("C1", 64, 3.0, 10), ("C1", 13, 2.0, 5), ("C2", 16, -0.5, 10),
+                                          ("C2", 6, 0.5, 3), ("C3", 12, 3.0, 10), ("J32", 20, 0.5, 6),
+                                          ("J10", 8, 4.0, 6), ("J6", 32, 2.0, 8)])
+@pytest.mark.parametrize("mode", [m.EXIT_NONE, m.EXIT_SYNDROME])
+def test_layered_i8_bit_exact_vs_oracle(oracle, key, F, snr, it, mode):
+    code, oc = load(oracle, key)
+    y = noisy(oracle, code.N, F, snr)
+    r = code.decode(y, it, schedule=m.SCHED_LAYERED, early_exit=mode, debug=True)
+    D, its, app, rec = orc_i8(oracle, oc, y, it, mode)
+    assert (r.iters == its).all()
+    assert (r.ok == D[code.N]).all()
+    assert (r.app == app).all(), "APP values differ"
+    assert (r.msgs == rec).all(), "check records (min1, min2, idx, signs) differ"
+    assert (r.D == D).all()
+
+
+@pytest.mark.parametrize("bnum,bshift,amax,scale", [(1, 2, 127, 8.0), (1, 3, 63, 4.0), (3, 4, 127, 16.0),
+                                                    (5, 5, 31, 8.0), (0, 0, 15, 2.0)])
+def test_layered_i8_scaling_and_clipping_variants(oracle, bnum, bshift, amax, scale):
+    code, oc = load(oracle, "C1")
+    y = noisy(oracle, code.N, 32, 2.5)
+    r = code.decode(y, 7, schedule=m.SCHED_LAYERED, debug=True, beta_num=bnum, beta_shift=bshift, msg_max=amax,
+                    llr_scale=scale)
+    D, its, app, rec = orc_i8(oracle, oc, y, 7, 0, scale, amax, bnum, bshift)
+    assert (r.app == app).all() and (r.msgs == rec).all() and (r.D == D).all()
+
+
+def test_layered_i8_io_variants(oracle):
+    code, oc = load(oracle, "C3")
+    F = 10
+    y = noisy(oracle, code.N, F, 3.0)
+    D, its, app, rec = orc_i8(oracle, oc, y, 6, 2)
+    r = code.decode(np.ascontiguousarray(y.T), 6, schedule=m.SCHED_LAYERED, layout=m.LAYOUT_FN, early_exit=2,
+                    out_format=m.OUT_U8)
+    assert (r.D.T == D[: code.N]).all() and (r.iters == its).all()
+    r = code.decode(y, 6, schedule=m.SCHED_LAYERED, early_exit=2, out_format=m.OUT_BITPACK)
+    bits = ((r.D[:, :, None] >> np.arange(32)[None, None, :]) & 1).reshape(F, -1)[:, : code.N]
+    assert (bits.T == D[: code.N]).all()
+    q = np.clip(np.rint(y * 8), -127, 127).astype(np.int8)
+    r = code.decode(q, 6, schedule=m.SCHED_LAYERED, early_exit=2, out_format=m.OUT_U8)
+    assert (r.D == D[: code.N]).all()
+
+
+def test_device_path_and_large_batch_properties(oracle):
+    """Device-resident I/O (torch tensors, no host copies) at a batch that fills the GPU; size-
+    independent checks: decoded words satisfy H x = 0 when flagged ok, equal frames decode equally,
+    and a slice re-decoded alone gives the same bits (no cross-frame leakage)."""
+    import torch
+    code, oc = load(oracle, "C2")
+    F = 1200
+    g = torch.Generator(device="cuda").manual_seed(7)
+    sigma = m.sigma_from_snr(0, 2.2, code.rate)
+    y = 1.0 + sigma * torch.randn(code.N, F, device="cuda", generator=g)
+    y[:, 5] = y[:, 3]
+    r = code.decode(y, 10, schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=m.OUT_U8, msg_max=31)
+    torch.cuda.synchronize()
+    D = r.D.cpu().numpy().astype(np.int32)
+    ok = r.ok.cpu().numpy()
+    assert ok.mean() > 0.5
+    assert (D[:, 5] == D[:, 3]).all()
+    chk = np.zeros(F, np.int32)
+    Dfull = np.concatenate([D, ok[None, :]], 0).astype(np.int32)
+    oracle.orc_syndrome_ok(oc.J, oc.L, oc.Z, ip(oc.H), ip(np.ascontiguousarray(Dfull)), F, ip(chk))
+    assert (chk == ok).all()
+    assert (D[:, ok == 1] == 0).all()  # all-zero codeword was sent
+    sub = code.decode(y[:, 40:52].contiguous(), 10, schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME,
+                      out_format=m.OUT_U8, msg_max=31)
+    assert (sub.D.cpu().numpy() == D[:, 40:52]).all()
+    # oracle on a few frames of the big batch
+    yo = y[:, :8].cpu().numpy()
+    Do, its, _, _ = orc_i8(oracle, oc, yo, 10, 2, amax=31)
+    assert (Do[: code.N] == D[:, :8]).all() and (its == r.iters.cpu().numpy()[:8]).all()

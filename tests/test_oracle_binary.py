@@ -114,7 +114,7 @@ def test_layered_modes_decode_clean_and_noisy(oracle):
     D32 = np.zeros((N + 1) * F, np.int32); it32 = np.zeros(F, np.int32)
     D8 = np.zeros((N + 1) * F, np.int32); it8 = np.zeros(F, np.int32)
     assert oracle.orc_layered_fp32(4, 24, 96, ip(code.H), fp(y), F, 10, 1.0, 2, ip(D32), ip(it32), None) == 0
-    assert oracle.orc_layered_i8(4, 24, 96, ip(code.H), fp(y), F, 10, 8.0, 127, 1, 0, 2, ip(D8), ip(it8), None,
+    assert oracle.orc_layered_i8(4, 24, 96, ip(code.H), fp(y), F, 10, 8.0, 127, 0, 0, 2, ip(D8), ip(it8), None,
                                  None) == 0
     ok32, ok8 = D32[N * F:], D8[N * F:]
     assert ok32.sum() >= 60 and ok8.sum() >= 58
