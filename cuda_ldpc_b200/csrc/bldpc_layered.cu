@@ -36,8 +36,63 @@ struct LayeredParams {
     float msg_max;
     float beta_mul;         // beta_num / 2^beta_shift
     float beta_bias;        // 0.5 - 2^-(beta_shift+1)
-    LayerTables lt;
+    int scale_on;           // beta_num != 0
+    unsigned c64;           // 0x64646464: kept in a register so PRMT can take the selector as its immediate
+    // kernel-ready layer tables: entry e = {column-block byte offset c*Z*4, shift byte offset s*4}
+    int2 tab[kMaxBlocks];
+    unsigned short off[kMaxLayers];
+    unsigned char dc[kMaxLayers];
+    LayerTables lt;         // compact form, used by the debug dump only
 };
+
+// Check records: 256-bit global accesses with the L2 evict-last policy (LDG.E.ELL2.256 /
+// STG.E.ELL2.256 on sm_100a) so that the per-CTA record slices stay L2-resident while the
+// channel values stream through; the trailing 128 bits of wide records use a plain access.
+template <int U4>
+__device__ __forceinline__ void rec_load(const uint4 *p, unsigned *rw)
+{
+    asm volatile("ld.global.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
+                 : "l"(p));
+    if (U4 == 3) {
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(rw[8]), "=r"(rw[9]), "=r"(rw[10]), "=r"(rw[11])
+                     : "l"(p + 2));
+    } else if (U4 == 4) {
+        asm volatile("ld.global.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(rw[8]), "=r"(rw[9]), "=r"(rw[10]), "=r"(rw[11]), "=r"(rw[12]), "=r"(rw[13]), "=r"(rw[14]),
+                       "=r"(rw[15])
+                     : "l"(p + 2));
+    }
+}
+template <int U4>
+__device__ __forceinline__ void rec_store(uint4 *p, const unsigned *rw)
+{
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(rw[0]), "r"(rw[1]),
+                 "r"(rw[2]), "r"(rw[3]), "r"(rw[4]), "r"(rw[5]), "r"(rw[6]), "r"(rw[7])
+                 : "memory");
+    if (U4 == 3) {
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p + 2), "r"(rw[8]), "r"(rw[9]), "r"(rw[10]),
+                     "r"(rw[11])
+                     : "memory");
+    } else if (U4 == 4) {
+        asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 2), "r"(rw[8]),
+                     "r"(rw[9]), "r"(rw[10]), "r"(rw[11]), "r"(rw[12]), "r"(rw[13]), "r"(rw[14]), "r"(rw[15])
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ unsigned lds32(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
 __device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2 *>(&u); }
@@ -80,112 +135,185 @@ __device__ __forceinline__ __half2 beta_scale(__half2 m, __half2 mul, __half2 nb
     return __hsub2(m, fl);
 }
 
+// Sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)), 10 edges per accumulator so the
+// value stays below 1024 and its bit pattern can be read off 1024 + acc.  Edge k of a degree-dc
+// check lives in sign word g = k/10 at bit (min(10, dc-10g) - 1 - (k-10g)) of each 16-bit lane.
+constexpr int kSignGroup = 10;
 template <int DCMAX>
 struct RecLayout {
-    static constexpr int SW = (DCMAX + 15) / 16;  // sign words per half-group
-    static constexpr int WORDS = 6 + 2 * SW;      // m1 x2, m2 x2, idx x2, signs
-    static constexpr int U4 = (WORDS + 3) / 4;
+    static constexpr int SW = (DCMAX + kSignGroup - 1) / kSignGroup;  // sign words per half-group
+    static constexpr int WORDS = 6 + 2 * SW;                          // m1 x2, m2 x2, idx x2, signs
+    static constexpr int U4 = (WORDS + 3) / 4;                        // uint4 moved per record (2..4)
+    static constexpr int STRIDE = U4 <= 2 ? 2 : 4;  // uint4 between records: every record 32-byte aligned
 };
+__host__ __device__ constexpr int sign_bit_pos(int dc, int k)
+{
+    const int g = k / kSignGroup, j = k - g * kSignGroup;
+    const int gs = (dc - g * kSignGroup) < kSignGroup ? (dc - g * kSignGroup) : kSignGroup;
+    return gs - 1 - j;
+}
 
 // One check row of one layer for the 4 codewords of the group.
-template <int DCMAX, bool FIRST, bool SCALE>
-__device__ __forceinline__ void process_row(unsigned char *app, const LayeredParams &p, int off, int dc, int i4,
-                                            int Z4, uint4 *recp, __half2 amax, __half2 bmul, __half2 nbias)
+// EXACT: the check degree is the template constant DC (no per-edge branches, every table entry is
+// a constant-bank load at an immediate offset, every shift amount is an immediate).  !EXACT: DC is
+// the bucket's maximum and edges k >= dc are predicated off (rare degrees only).
+//
+// Pipe balance (ncu: the ALU pipe is the binding one, profiles/r01_*): selects, index tracking and
+// the sign/parity collection run as HFMA2 / HADD2 / HSET2.BF on the FMA pipe; only the byte
+// shuffles (PRMT), the sign XORs (LOP3) and the fp16 min/max (HMNMX2) stay on the ALU pipe.
+//
+// Works on t' = t + 1152 so that the re-biasing add of the store path disappears:
+//   a' = 1152 + APP (the PRMT result read as fp16),  t' = a' - c2v_old,  t = t' - 1152,
+//   APP'_biased_fp16 = clamp(t' + c2v_new, 1025, 1279).
+template <int DC, int DCHI, bool FIRST, bool EXACT>
+__device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParams &p, int off, int dc_rt, int i4,
+                                              int Z4, uint4 *recp, __half2 amax, __half2 bmul, __half2 nbias)
 {
-    constexpr int SW = RecLayout<DCMAX>::SW;
-    constexpr int U4 = RecLayout<DCMAX>::U4;
+    constexpr int SW = RecLayout<DCHI>::SW;  // record layout of the kernel's degree bucket
+    constexpr int U4 = RecLayout<DCHI>::U4;
+    const int dc = EXACT ? DC : dc_rt;
     unsigned rw[U4 * 4];
+    if (!FIRST) rec_load<U4>(recp, rw);
+    // record words: [0,1] m1 (frames 01, 23)  [2,3] m2  [4,5] idx  [6 + h*SW + g] sign words
+    const __half2 k1152 = __float2half2_rn(1152.0f), k1024 = __float2half2_rn(1024.0f);
+    const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f);
+    __half2 dold[2];
     if (!FIRST) {
-#pragma unroll
-        for (int q = 0; q < U4; q++) {
-            const uint4 v = recp[q];
-            rw[4 * q] = v.x;
-            rw[4 * q + 1] = v.y;
-            rw[4 * q + 2] = v.z;
-            rw[4 * q + 3] = v.w;
-        }
+        dold[0] = __hsub2(u2h(rw[2]), u2h(rw[0]));
+        dold[1] = __hsub2(u2h(rw[3]), u2h(rw[1]));
     }
-    // record words: [0,1] m1 (lo,hi)  [2,3] m2  [4,5] idx  [6 + h*SW + w] sign bits, edge k at
-    // bit 15-(k%16) of each 16-bit lane of word k/16
-    __half2 t[2][DCMAX];
-    int addr[DCMAX];
+    unsigned addr[DC];
+    __half2 tp[2][DC];
     __half2 min1[2] = {amax, amax}, min2[2] = {amax, amax};
-    unsigned idx[2] = {0u, 0u};
-    unsigned sacc[2][SW];
-    unsigned pacc[2] = {0u, 0u};
+    __half2 idx[2] = {zero, zero}, cnt[2] = {zero, zero};
+    __half2 sacc[2][SW];
 #pragma unroll
     for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int w = 0; w < SW; w++) sacc[h][w] = 0u;
-
+        for (int g = 0; g < SW; g++) sacc[h][g] = zero;
 #pragma unroll
-    for (int k = 0; k < DCMAX; k++) {
-        if (k < dc) {
-            const int e = off + k;
-            int col4 = i4 + 4 * (int)p.lt.shift[e];
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < dc) {
+            const __half2 kh = __float2half2_rn((float)k);
+            const int2 e = p.tab[off + k];
+            int col4 = i4 + e.y;
             col4 -= (col4 >= Z4) ? Z4 : 0;
-            addr[k] = (int)p.lt.col[e] * Z4 + col4;
-            const unsigned w = *reinterpret_cast<const unsigned *>(app + addr[k]);
-            const unsigned kh = h2u(__float2half2_rn((float)k));
+            addr[k] = sbase + (unsigned)(e.x + col4);
+            const unsigned wk = lds32(addr[k]);
+            const int sh = 15 - sign_bit_pos(dc, k);  // brings edge k's sign bit to bit 15 of each lane
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const __half2 a = h ? unpack_hi(w) : unpack_lo(w);
-                __half2 tt;
-                if (FIRST) {
-                    tt = a;
-                } else {
-                    const unsigned msk = __heq2_mask(u2h(rw[4 + h]), u2h(kh));
-                    const unsigned mag = sel(msk, rw[2 + h], rw[h]);
-                    const unsigned sg = (rw[6 + h * SW + (k >> 4)] << (k & 15)) & 0x80008000u;
-                    tt = __hsub2(a, u2h(mag ^ sg));
+                __half2 t1 = u2h(prmt(wk, p.c64, h ? 0x4342u : 0x4140u));
+                if (!FIRST) {
+                    const __half2 mag = __hfma2(__heq2(u2h(rw[4 + h]), kh), dold[h], u2h(rw[h]));
+                    const unsigned sg = (rw[6 + h * SW + k / kSignGroup] << sh) & 0x80008000u;
+                    t1 = __hsub2(t1, u2h(h2u(mag) ^ sg));
                 }
-                t[h][k] = tt;
-                const unsigned tu = h2u(tt);
+                tp[h][k] = t1;
+                const __half2 tt = __hsub2(t1, k1152);
                 const __half2 ab = __hmin2(__habs2(tt), amax);
-                pacc[h] ^= tu;
-                sacc[h][k >> 4] |= (tu >> (k & 15)) & (0x80008000u >> (k & 15));
-                const unsigned lt = __hlt2_mask(ab, min1[h]);
-                idx[h] = sel(lt, kh, idx[h]);
+                const __half2 neg = __hlt2(tt, zero);  // 1.0 where t < 0 (t is never -0)
+                sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
+                cnt[h] = __hadd2(cnt[h], neg);
+                const __half2 lt = __hlt2(ab, min1[h]);
+                idx[h] = __hfma2(lt, __hsub2(kh, idx[h]), idx[h]);
                 min2[h] = __hmin2(min2[h], __hmax2(min1[h], ab));
                 min1[h] = __hmin2(min1[h], ab);
             }
         }
     }
     unsigned nsg[2][SW];
+    __half2 dnew[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        if (SCALE) {
+        if (p.scale_on) {
             min1[h] = beta_scale(min1[h], bmul, nbias);
             min2[h] = beta_scale(min2[h], bmul, nbias);
         }
-        const unsigned pm = prmt(pacc[h], 0u, 0xBB99u);  // 0xFFFF per lane whose parity is odd
+        dnew[h] = __hsub2(min2[h], min1[h]);
+        // parity of the negative-sign count -> 0xFFFF per lane; sign bits of all dc edges flip with it
+        const unsigned pm = (h2u(__hadd2(cnt[h], k1024)) & 0x00010001u) * 0xFFFFu;
 #pragma unroll
-        for (int w = 0; w < SW; w++) nsg[h][w] = sacc[h][w] ^ pm;
+        for (int g = 0; g < SW; g++) {
+            int gs = dc - g * kSignGroup;
+            gs = gs < 0 ? 0 : (gs > kSignGroup ? kSignGroup : gs);
+            const unsigned gm = ((1u << gs) - 1u) * 0x00010001u;
+            nsg[h][g] = (h2u(__hadd2(sacc[h][g], k1024)) ^ pm) & gm;
+        }
         rw[h] = h2u(min1[h]);
         rw[2 + h] = h2u(min2[h]);
-        rw[4 + h] = idx[h];
+        rw[4 + h] = h2u(idx[h]);
 #pragma unroll
-        for (int w = 0; w < SW; w++) rw[6 + h * SW + w] = nsg[h][w];
+        for (int g = 0; g < SW; g++) rw[6 + h * SW + g] = nsg[h][g];
     }
-#pragma unroll
-    for (int q = 0; q < U4; q++) recp[q] = make_uint4(rw[4 * q], rw[4 * q + 1], rw[4 * q + 2], rw[4 * q + 3]);
+    rec_store<U4>(recp, rw);
 
-    const __half2 lim = __float2half2_rn(127.0f), nlim = __float2half2_rn(-127.0f);
+    const __half2 hi = __float2half2_rn(1279.0f), lo = __float2half2_rn(1025.0f);
 #pragma unroll
-    for (int k = 0; k < DCMAX; k++) {
-        if (k < dc) {
-            const unsigned kh = h2u(__float2half2_rn((float)k));
-            __half2 v[2];
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < dc) {
+            const __half2 kh = __float2half2_rn((float)k);
+            const int sh = 15 - sign_bit_pos(dc, k);
+            unsigned v[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const unsigned msk = __heq2_mask(u2h(idx[h]), u2h(kh));
-                const unsigned mag = sel(msk, h2u(min2[h]), h2u(min1[h]));
-                const unsigned sg = (nsg[h][k >> 4] << (k & 15)) & 0x80008000u;
-                __half2 x = __hadd2(t[h][k], u2h(mag ^ sg));
-                v[h] = __hmin2(__hmax2(x, nlim), lim);
+                const __half2 mag = __hfma2(__heq2(idx[h], kh), dnew[h], min1[h]);
+                const unsigned sg = (nsg[h][k / kSignGroup] << sh) & 0x80008000u;
+                const __half2 x = __hadd2(tp[h][k], u2h(h2u(mag) ^ sg));
+                v[h] = h2u(__hmin2(__hmax2(x, lo), hi));
             }
-            *reinterpret_cast<unsigned *>(app + addr[k]) = pack4(v[0], v[1]);
+            sts32(addr[k], prmt(v[0], v[1], 0x6420u));
         }
+    }
+}
+
+// Rows of a layer whose degree is outside the exact range of the kernel's bucket.  Out of line so
+// that its register needs do not leak into the allocation of the hot exact-degree paths.
+template <int DCHI, bool FIRST>
+__device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *recl,
+                                          __half2 amax, __half2 bmul, __half2 nbias)
+{
+    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    const int Z = p.Z, Z4 = 4 * Z;
+    for (int i = threadIdx.x; i < Z; i += blockDim.x)
+        process_row_x<DCHI, DCHI, FIRST, false>(sbase, p, off, dc, 4 * i, Z4, recl + (size_t)i * RS, amax, bmul, nbias);
+}
+
+// One full iteration: all layers in order, the Z rows of a layer spread over the CTA.
+template <int DCHI, bool FIRST>
+__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec,
+                                             __half2 amax, __half2 bmul, __half2 nbias)
+{
+    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
+    for (int r = 0; r < p.J; r++) {
+        const int dc = p.dc[r], off = p.off[r];
+        uint4 *recl = rec + (size_t)r * Z * RS;
+        // the records of the NEXT layer (next iteration's first layer after the last one) are read a
+        // whole layer from now: pull them into L1 so the row loop never waits on L2/HBM
+        if (!FIRST || r == p.J - 1) {
+            const uint4 *nxt = rec + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
+            for (int i = tid; i < Z; i += T) {
+                prefetch_l1(nxt + (size_t)i * RS);
+                if (RecLayout<DCHI>::U4 > 2) prefetch_l1(nxt + (size_t)i * RS + 2);
+            }
+        }
+#define LDPC_ROWS(DCX)                                                                                        \
+    for (int i = tid; i < Z; i += T)                                                                          \
+        process_row_x<DCX, DCHI, FIRST, true>(sbase, p, off, DCX, 4 * i, Z4, recl + (size_t)i * RS, amax, bmul, nbias);
+        if (dc == DCHI) {
+            LDPC_ROWS(DCHI)
+        } else if (DCHI >= 2 && dc == DCHI - 1) {
+            LDPC_ROWS((DCHI >= 2 ? DCHI - 1 : 1))
+        } else if (DCHI >= 3 && dc == DCHI - 2) {
+            LDPC_ROWS((DCHI >= 3 ? DCHI - 2 : 1))
+        } else if (DCHI >= 4 && dc == DCHI - 3) {
+            LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
+        } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amax, bmul, nbias);
+        }
+#undef LDPC_ROWS
+        __syncthreads();
     }
 }
 
@@ -252,10 +380,11 @@ template <int DCMAX>
 __device__ void dump_records(const LayeredParams &p, const uint4 *rec, int g, unsigned fmask)
 {
     constexpr int SW = RecLayout<DCMAX>::SW;
-    constexpr int U4 = RecLayout<DCMAX>::U4;
+    constexpr int RS = RecLayout<DCMAX>::STRIDE;
     const unsigned *rw = reinterpret_cast<const unsigned *>(rec);
     for (int m = threadIdx.x; m < p.M; m += blockDim.x) {
-        const unsigned *r = rw + (size_t)m * U4 * 4;
+        const unsigned *r = rw + (size_t)m * RS * 4;
+        const int dc = p.dc[m / p.Z];
         for (int j = 0; j < 4; j++) {
             if (!((fmask >> j) & 1u)) continue;
             const int h = j >> 1, sh = (j & 1) * 16;
@@ -263,10 +392,8 @@ __device__ void dump_records(const LayeredParams &p, const uint4 *rec, int g, un
             const __half m2 = __ushort_as_half((unsigned short)(r[2 + h] >> sh));
             const __half ix = __ushort_as_half((unsigned short)(r[4 + h] >> sh));
             unsigned sg = 0;
-            for (int k = 0; k < DCMAX; k++)
-                sg |= ((r[6 + h * SW + (k >> 4)] >> (sh + 15 - (k & 15))) & 1u) << k;
-            const int dc = p.lt.dc[m / p.Z];
-            sg &= (dc >= 32) ? 0xffffffffu : ((1u << dc) - 1u);
+            for (int k = 0; k < dc; k++)
+                sg |= ((r[6 + h * SW + k / kSignGroup] >> (sh + sign_bit_pos(dc, k))) & 1u) << k;
             const size_t f = (size_t)4 * g + j;
             p.dbg_rec[((size_t)m * 4 + 0) * p.F + f] = (unsigned)__half2int_rn(m1);
             p.dbg_rec[((size_t)m * 4 + 1) * p.F + f] = (unsigned)__half2int_rn(m2);
@@ -279,10 +406,10 @@ __device__ void dump_records(const LayeredParams &p, const uint4 *rec, int g, un
 // threads per CTA are capped so that the per-row register arrays (2*DCMAX + DCMAX) never spill
 template <int DCMAX>
 struct ThreadCap {
-    static constexpr int value = DCMAX <= 8 ? 640 : (DCMAX <= 16 ? 512 : 384);
+    static constexpr int value = DCMAX <= 12 ? 640 : (DCMAX <= 24 ? 512 : 384);
 };
 
-template <int DCMAX, bool SCALE>
+template <int DCMAX>
 __global__ void __launch_bounds__(ThreadCap<DCMAX>::value, 1)
 ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 {
@@ -291,8 +418,8 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     __shared__ unsigned s_fail;
     const int tid = threadIdx.x, T = blockDim.x;
     const int N = p.N, Z = p.Z, F = p.F, Z4 = 4 * Z;
-    constexpr int U4 = RecLayout<DCMAX>::U4;
-    uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * U4;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * RecLayout<DCMAX>::STRIDE;
     const __half2 amax = __float2half2_rn(p.msg_max);
     const __half2 bmul = __float2half2_rn(p.beta_mul);
     const __half2 nbias = __float2half2_rn(-p.beta_bias);
@@ -345,17 +472,10 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         int it = 0;
         while (it < p.iters) {
             it++;
-            for (int r = 0; r < p.J; r++) {
-                const int dc = p.lt.dc[r], off = p.lt.off[r];
-                for (int i = tid; i < Z; i += T) {
-                    uint4 *recp = rec + (size_t)(r * Z + i) * U4;
-                    if (it == 1)
-                        process_row<DCMAX, true, SCALE>(smem, p, off, dc, 4 * i, Z4, recp, amax, bmul, nbias);
-                    else
-                        process_row<DCMAX, false, SCALE>(smem, p, off, dc, 4 * i, Z4, recp, amax, bmul, nbias);
-                }
-                __syncthreads();
-            }
+            if (it == 1)
+                sweep_layers<DCMAX, true>(sbase, p, rec, amax, bmul, nbias);
+            else
+                sweep_layers<DCMAX, false>(sbase, p, rec, amax, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 unsigned fail = 0u;
                 for (int r = 0; r < p.J; r++) {
@@ -390,75 +510,66 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     }
 }
 
-template <int DCMAX>
-static int launch_i8(const ldpc_code *c, LayeredParams &p, bool scale, int threads, int grid, size_t smem,
-                     cudaStream_t st)
-{
-    if (scale) {
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(ldpc_layered_i8_kernel<DCMAX, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ldpc_layered_i8_kernel<DCMAX, true><<<grid, threads, smem, st>>>(p);
-    } else {
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(ldpc_layered_i8_kernel<DCMAX, false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ldpc_layered_i8_kernel<DCMAX, false><<<grid, threads, smem, st>>>(p);
+// host-side dispatch over the degree buckets (DCHI = dc_max rounded up to a multiple of 4)
+template <int DCHI>
+struct I8Kernel {
+    static int occupancy(int threads, size_t smem, int *out)
+    {
+        LDPC_CUDA_TRY(cudaFuncSetAttribute(ldpc_layered_i8_kernel<DCHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ldpc_layered_i8_kernel<DCHI>, threads, smem));
+        return LDPC_OK;
     }
-    LDPC_CUDA_TRY(cudaGetLastError());
-    return LDPC_OK;
-}
+    static int launch(const LayeredParams &p, int threads, int grid, size_t smem, cudaStream_t st)
+    {
+        ldpc_layered_i8_kernel<DCHI><<<grid, threads, smem, st>>>(p);
+        LDPC_CUDA_TRY(cudaGetLastError());
+        return LDPC_OK;
+    }
+};
 
-template <int DCMAX>
-static int occupancy_i8(bool scale, int threads, size_t smem, int *out)
-{
-    if (scale) {
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(ldpc_layered_i8_kernel<DCMAX, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ldpc_layered_i8_kernel<DCMAX, true>, threads,
-                                                                    smem));
-    } else {
-        LDPC_CUDA_TRY(cudaFuncSetAttribute(ldpc_layered_i8_kernel<DCMAX, false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, ldpc_layered_i8_kernel<DCMAX, false>,
-                                                                    threads, smem));
-    }
-    return LDPC_OK;
-}
+#ifndef LDPC_BUCKETS
+#define LDPC_BUCKETS(X) X(4) X(8) X(12) X(16) X(20) X(24) X(28) X(32)
+#endif
 
 struct I8Plan {
     int dcb, threads, grid, u4;
     size_t smem;
 };
 
-static int plan_i8(const ldpc_code *c, int F, bool scale, I8Plan *pl)
+static int plan_i8(const ldpc_code *c, int F, I8Plan *pl)
 {
     pl->smem = (size_t)c->N * 4;
     if (pl->smem > 227 * 1024) return LDPC_ERR_UNSUPPORTED;  // N > 58112: one group does not fit one SM
-    pl->dcb = c->dc_max <= 8 ? 8 : (c->dc_max <= 16 ? 16 : (c->dc_max <= 24 ? 24 : 32));
-    // threads: the Z rows of a layer spread over whole warps, at most ThreadCap<DCMAX> threads
-    const int cap = pl->dcb == 8 ? ThreadCap<8>::value : pl->dcb == 16 ? ThreadCap<16>::value : ThreadCap<24>::value;
-    const int rows_per_thread = (c->Z + cap - 1) / cap;
-    int threads = (c->Z + rows_per_thread - 1) / rows_per_thread;
-    pl->threads = (threads + 31) & ~31;
-    int occ = 0, rc;
+    pl->dcb = (c->dc_max + 3) & ~3;
+    int cap = 0, occ = 0, rc = LDPC_ERR_UNSUPPORTED;
     switch (pl->dcb) {
-        case 8: rc = occupancy_i8<8>(scale, pl->threads, pl->smem, &occ); break;
-        case 16: rc = occupancy_i8<16>(scale, pl->threads, pl->smem, &occ); break;
-        case 24: rc = occupancy_i8<24>(scale, pl->threads, pl->smem, &occ); break;
-        default: rc = occupancy_i8<32>(scale, pl->threads, pl->smem, &occ); break;
+#define X(D) case D: cap = ThreadCap<D>::value; pl->u4 = RecLayout<D>::STRIDE; break;
+        LDPC_BUCKETS(X)
+#undef X
+        default: return LDPC_ERR_UNSUPPORTED;
+    }
+    // threads: the Z rows of a layer spread over whole warps, at most ThreadCap<DCHI> threads
+    const int rows_per_thread = (c->Z + cap - 1) / cap;
+    const int threads = (c->Z + rows_per_thread - 1) / rows_per_thread;
+    pl->threads = (threads + 31) & ~31;
+    switch (pl->dcb) {
+#define X(D) case D: rc = I8Kernel<D>::occupancy(pl->threads, pl->smem, &occ); break;
+        LDPC_BUCKETS(X)
+#undef X
     }
     if (rc != LDPC_OK) return rc;
     if (occ < 1) return LDPC_ERR_UNSUPPORTED;
     const int groups = (F + 3) / 4;
     pl->grid = c->num_sms * occ;
     if (pl->grid > groups) pl->grid = groups;
-    pl->u4 = pl->dcb == 8 ? RecLayout<8>::U4 : pl->dcb == 16 ? RecLayout<16>::U4 : pl->dcb == 24 ? RecLayout<24>::U4 : RecLayout<32>::U4;
     return LDPC_OK;
 }
 
-int layered_i8_scratch_bytes(const ldpc_code *c, int F, int beta_num, size_t *bytes)
+int layered_i8_scratch_bytes(const ldpc_code *c, int F, int, size_t *bytes)
 {
     I8Plan pl;
-    int rc = plan_i8(c, F, beta_num != 0, &pl);
+    int rc = plan_i8(c, F, &pl);
     if (rc != LDPC_OK) return rc;
     *bytes = (size_t)pl.grid * c->M * pl.u4 * sizeof(uint4);
     return LDPC_OK;
@@ -469,9 +580,8 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     if (a.msg_max < 1 || a.msg_max > 127 || a.beta_num < 0 || a.beta_num > 8 || a.beta_shift < 0 ||
         a.beta_shift > 7 || (a.beta_num != 0 && a.beta_num >= (1 << a.beta_shift)))
         return LDPC_ERR_ARG;
-    const bool scale = a.beta_num != 0;
     I8Plan pl;
-    int rc = plan_i8(c, a.F, scale, &pl);
+    int rc = plan_i8(c, a.F, &pl);
     if (rc != LDPC_OK) return rc;
     if ((size_t)pl.grid * c->M * pl.u4 * sizeof(uint4) > a.scratch_bytes) return LDPC_ERR_NOMEM;
     LayeredParams p;
@@ -498,12 +608,21 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.msg_max = (float)a.msg_max;
     p.beta_mul = (float)a.beta_num / (float)(1 << a.beta_shift);
     p.beta_bias = 0.5f - 1.0f / (float)(2 << a.beta_shift);
+    p.scale_on = a.beta_num != 0;
+    p.c64 = 0x64646464u;
     p.lt = c->lt;
+    for (int r = 0; r < c->J; r++) {
+        p.off[r] = c->lt.off[r];
+        p.dc[r] = c->lt.dc[r];
+        for (int k = 0; k < c->lt.dc[r]; k++) {
+            const int e = c->lt.off[r] + k;
+            p.tab[e] = make_int2((int)c->lt.col[e] * c->Z * 4, (int)c->lt.shift[e] * 4);
+        }
+    }
     switch (pl.dcb) {
-        case 8: rc = launch_i8<8>(c, p, scale, pl.threads, pl.grid, pl.smem, st); break;
-        case 16: rc = launch_i8<16>(c, p, scale, pl.threads, pl.grid, pl.smem, st); break;
-        case 24: rc = launch_i8<24>(c, p, scale, pl.threads, pl.grid, pl.smem, st); break;
-        default: rc = launch_i8<32>(c, p, scale, pl.threads, pl.grid, pl.smem, st); break;
+#define X(D) case D: rc = I8Kernel<D>::launch(p, pl.threads, pl.grid, pl.smem, st); break;
+        LDPC_BUCKETS(X)
+#undef X
     }
     if (rc == LDPC_OK) *launches += 1;
     return rc;

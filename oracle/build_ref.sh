@@ -15,6 +15,9 @@ set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF_ROOT:-/root/reference}/bldpc_实习"
 [ -d "$REF" ] || { echo "reference tree not present ($REF) — keeping prebuilt oracle/_ref" >&2; exit 0; }
+# REF_HFILE_DIR: directory the built library reads its H file from at run time (default: the
+# reference tree; builds that must run on the GPU box point it at the repo's data copy).
+HDIR="${REF_HFILE_DIR:-$REF}"
 name=$1; J=$2; L=$3; Z=$4; hfile=$5; F=$6; maxit=$7; least=$8; snrtype=$9; variant=${10:-literal}
 out="$here/_ref"; mkdir -p "$out"; tmp="$(mktemp -d)"; trap 'rm -rf "$tmp"' EXIT
 CXX=/usr/bin/g++
@@ -25,7 +28,7 @@ fix='s/__NOFIX__//'
 for src in Simulation LDPC_Decoder LDPC_Encoder; do
   tr -d '\r' < "$REF/$src.cu" \
    | sed -E 's/([A-Za-z_]+)<<<([^,]+),\s*([^>]+)>>>\((.*)\);/SHIM_LAUNCH(\1, \2, \3, \4);/' \
-   | sed "s|char file\[100\] = \"PON_LDPC.txt\";|char file[200] = \"$REF/$hfile\";|" \
+   | sed "s|char file\[100\] = \"PON_LDPC.txt\";|char file[200] = \"$HDIR/$hfile\";|" \
    | sed 's/float Add_result;/float Add_result = 0;/' \
    | sed "$fix" \
    | $CXX -x c++ $flags -c -o "$tmp/$src.o" -
