@@ -68,3 +68,38 @@ class OracleCode:
 @pytest.fixture(scope="session")
 def data_dir():
     return DATA
+
+
+NB_DATA = os.path.join(DATA, "nbldpc")
+
+
+@pytest.fixture(scope="session")
+def gf_dir(tmp_path_factory):
+    """GF table files regenerated from the primitive polynomials (cuda_ldpc_b200/gf.py)."""
+    from cuda_ldpc_b200.gf import write_table_file
+    d = tmp_path_factory.mktemp("gf")
+    for q in (16, 64, 256):
+        write_table_file(q, str(d / f"Arith.Table.GF.{q}.txt"))
+    return str(d)
+
+
+@pytest.fixture(scope="session")
+def nb_oracle(oracle):
+    lib = oracle
+    lib.nb_orc_load.restype = C.c_void_p
+    lib.nb_orc_load.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    lib.nb_orc_free.argtypes = [C.c_void_p]
+    lib.nb_orc_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.nb_orc_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib.nb_orc_constellation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nb_orc_syndrome_ok.argtypes = [C.c_void_p, C.c_void_p]
+    lib.nb_orc_sigma.restype = C.c_float
+    lib.nb_orc_sigma.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    lib.nb_orc_awgn.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+    lib.nb_orc_modulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nb_orc_demodulate.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.nb_orc_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p]
+    lib.nb_orc_decode_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
