@@ -1,0 +1,610 @@
+// Batched GF(q) LDPC decoding: EMS, trellis min-max (TMM) and layered TMM, one CTA per frame,
+// one launch per batch.  Replaces Demodulate + Decoding_EMS(_GPU) / Decoding_TMM(_GPU) /
+// Decoding_layered_TMM (NB/src/LDPC_Decoder.cpp:132-702, NB/src/Decode_GPU.cu:138-1070), which
+// decode ONE frame per call with a kernel launch per node phase, cudaMalloc/cudaFree, in-kernel
+// malloc and a D2H copy + host syndrome check per iteration.
+//
+// Numerics: fp32, same operation order as the oracle (oracle/nb_oracle.c, `fresh` EMS sums;
+// TMM bit-for-bit the reference's order), --fmad=false, the 1/1.2 and 0.8 scalings in double
+// like the reference (NB/src/LDPC_Decoder.cpp:309,519).
+#include <float.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "nb_common.h"
+
+namespace ldpcb {
+
+constexpr int kNbThreads = 256;
+constexpr int kNmMax = 4;  // EMS_NM supported on the device path
+
+struct NbParams {
+    const void *in;
+    uint16_t *out;
+    int *iters_out, *ok_out;
+    float *scratch;        // per CTA slot
+    size_t slot_floats;
+    int F, N, M, q, p, dv_max, dc_max, n_const;
+    int algo, in_kind, maxit, nm, nc;
+    float sigma;
+    int ems_chunk;         // EMS check tasks per shared-memory chunk
+    const uint16_t *mul, *inv;
+    const int *vw, *cw, *v_cn, *v_pos, *c_vn, *c_gf, *c_pos;
+    const float *cre, *cim;
+};
+
+__device__ __forceinline__ int gmul(const NbParams &p, int a, int b) { return __ldg(p.mul + a * p.q + b); }
+
+// ---- Demodulate, NB/src/LDPC_Decoder.cpp:132-171 -------------------------------------------------
+__device__ void demodulate(const NbParams &p, int f, float *lch)
+{
+    const int q = p.q, N = p.N, tid = threadIdx.x, T = blockDim.x;
+    if (p.in_kind == NB_IN_SYMBOL_LLR) {
+        const float *src = reinterpret_cast<const float *>(p.in) + (size_t)f * N * (q - 1);
+        for (int i = tid; i < N * (q - 1); i += T) lch[i] = src[i];
+    } else if (p.in_kind == NB_IN_BPSK) {
+        const float *rx = reinterpret_cast<const float *>(p.in) + (size_t)f * N * p.p;
+        const float s2 = __fmul_rn(p.sigma, p.sigma);
+        for (int i = tid; i < N * (q - 1); i += T) {
+            const int s = i / (q - 1), a = i - s * (q - 1) + 1;
+            float v = 0.0f;
+            for (int b = 0; b < p.p; b++)
+                if (a & (1 << b)) v = __fadd_rn(v, __fdiv_rn(__fmul_rn(-2.0f, rx[s * p.p + b]), s2));
+            lch[i] = v;
+        }
+    } else {
+        const float *rx = reinterpret_cast<const float *>(p.in) + (size_t)f * N * 2;
+        const float den = __fmul_rn(__fmul_rn(2.0f, p.sigma), p.sigma);
+        const float c0r = p.cre[0], c0i = p.cim[0];
+        for (int i = tid; i < N * (q - 1); i += T) {
+            const int s = i / (q - 1), a = i - s * (q - 1) + 1;
+            const float yr = rx[2 * s], yi = rx[2 * s + 1], car = p.cre[a], cai = p.cim[a];
+            const float tr = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, yr), c0r), car), __fsub_rn(car, c0r));
+            const float ti = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, yi), c0i), cai), __fsub_rn(cai, c0i));
+            lch[i] = __fdiv_rn(__fadd_rn(tr, ti), den);
+        }
+    }
+}
+
+// syndrome of the decided symbols; sets *fail != 0 when any check is violated
+__device__ void syndrome(const NbParams &p, const uint16_t *sym, int *fail)
+{
+    for (int row = threadIdx.x; row < p.M; row += blockDim.x) {
+        int s = 0;
+        for (int i = 0; i < p.cw[row]; i++)
+            s ^= gmul(p, sym[p.c_vn[row * p.dc_max + i]], p.c_gf[row * p.dc_max + i]);
+        if (s) *fail = 1;
+    }
+}
+
+// ---- EMS, NB/src/LDPC_Decoder.cpp:172-359 -------------------------------------------------------
+// One (check, output edge) task: E[s] = max over conf(q,1) U conf(Nm,Nc) of the fresh sum.
+// E lives in shared memory, transposed (E[a*stride + slot]) so that threads hit distinct banks.
+__device__ void ems_check_task(const NbParams &p, int row, int dc, const float *v2c, const uint16_t *topsym,
+                               const float *topval, float *c2v, float *E, int stride)
+{
+    const int q = p.q, w = p.cw[row];
+    for (int a = 0; a < q; a++) E[a * stride] = -INFINITY;
+    // inputs in ascending edge position, the output edge left out
+    int n = 0;
+    int ie[32], ih[32];
+    for (int b = 0; b < w; b++) {
+        if (b == dc) continue;
+        ie[n] = p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b];  // edge slot in v2c/top
+        ih[n] = p.c_gf[row * p.dc_max + b];
+        n++;
+    }
+    // conf(q,1): every input at its best symbol, at most one input at any other symbol
+    int s0 = 0;
+    for (int j = 0; j < n; j++) s0 ^= gmul(p, topsym[ie[j] * kNmMax], ih[j]);
+    {
+        float sum = 0.0f;
+        for (int j = 0; j < n; j++) sum = __fadd_rn(sum, topval[ie[j] * kNmMax]);
+        if (sum > E[s0 * stride]) E[s0 * stride] = sum;
+    }
+    for (int j = 0; j < n; j++) {
+        const int best = topsym[ie[j] * kNmMax];
+        const int sj = s0 ^ gmul(p, best, ih[j]);
+        const float *vj = v2c + (size_t)ie[j] * q;
+        for (int a = 0; a < q; a++) {
+            if (a == best) continue;
+            float sum = 0.0f;
+            for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? vj[a] : topval[ie[i] * kNmMax]);
+            const int s = sj ^ gmul(p, a, ih[j]);
+            if (sum > E[s * stride]) E[s * stride] = sum;
+        }
+    }
+    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1 (odometer with pruning)
+    const int Nc = (p.nc == p.dc_max - 1) ? w - 1 : p.nc;  // :297-304
+    int ks[32];
+    for (int j = 0; j < n; j++) ks[j] = 0;
+    while (true) {
+        int s = 0;
+        float sum = 0.0f;
+        for (int j = 0; j < n; j++) {
+            s ^= gmul(p, topsym[ie[j] * kNmMax + ks[j]], ih[j]);
+            sum = __fadd_rn(sum, topval[ie[j] * kNmMax + ks[j]]);
+        }
+        if (sum > E[s * stride]) E[s * stride] = sum;
+        int j = n - 1;
+        for (; j >= 0; j--) {
+            ks[j]++;
+            int diff = 0;
+            for (int i = 0; i <= j; i++) diff += ks[i] != 0;
+            if (ks[j] < p.nm && diff <= Nc) break;
+            ks[j] = 0;
+        }
+        if (j < 0) break;
+    }
+    const int h = p.c_gf[row * p.dc_max + dc];
+    float *m = c2v + ((size_t)row * p.dc_max + dc) * q;
+    const float e0 = E[0];
+    for (int k = 1; k < q; k++) {
+        const float d = __fsub_rn(E[gmul(p, k, h) * stride], e0);
+        m[k - 1] = (float)((double)d / 1.2);  // float difference, double division (:309)
+    }
+}
+
+__device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, float *c2v, float *v2c, float *topval,
+                           uint16_t *topsym, uint16_t *sym, float *smemE, int *s_fail)
+{
+    const int q = p.q, N = p.N, M = p.M, tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 0.0f;
+    __syncthreads();
+    int it = 0, ok = 0;
+    while (it < p.maxit) {
+        it++;
+        // variable nodes: LLR = L_ch + sum_d c2v_d, decide (DecideLLRVector :71-91)
+        for (int i = tid; i < N * (q - 1); i += T) {
+            const int col = i / (q - 1), a = i - col * (q - 1);
+            float v = lch[i];
+            for (int d = 0; d < p.vw[col]; d++)
+                v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + a]);
+            LLR[col * q + a] = v;
+        }
+        if (tid == 0) *s_fail = 0;
+        __syncthreads();
+        for (int col = tid; col < N; col += T) {
+            float mx = 0.0f;
+            int best = 0;
+            for (int a = 0; a < q - 1; a++)
+                if (LLR[col * q + a] > mx) {
+                    mx = LLR[col * q + a];
+                    best = a + 1;
+                }
+            sym[col] = (uint16_t)((mx <= 0.0f) ? 0 : best);
+        }
+        __syncthreads();
+        syndrome(p, sym, s_fail);
+        __syncthreads();
+        if (*s_fail == 0) {
+            ok = 1;
+            it--;  // the reference returns iterations-1 on success (:236)
+            break;
+        }
+        // v2c = LLR - c2v by symbol (symbol 0 = 0), and the first Nm entries of the stable descending
+        // sort of the list [1, 2, ..., q-1, 0] (BubleSort :17-36)
+        for (int e = tid; e < N * p.dv_max; e += T) {
+            const int col = e / p.dv_max, d = e - col * p.dv_max;
+            if (d >= p.vw[col]) continue;
+            const float *m = c2v + ((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q;
+            float *v = v2c + (size_t)e * q;
+            float tv[kNmMax];
+            int ts[kNmMax];
+            for (int k = 0; k < kNmMax; k++) {
+                tv[k] = -INFINITY;
+                ts[k] = -1;
+            }
+            for (int i = 0; i < q; i++) {
+                const int a = (i < q - 1) ? i + 1 : 0;
+                const float x = (a == 0) ? 0.0f : __fsub_rn(LLR[col * q + a - 1], m[a - 1]);
+                v[a] = x;
+                // insert behind every entry that is >= x (ties keep list order)
+                int pos = p.nm;
+                for (int k = p.nm - 1; k >= 0; k--)
+                    if (ts[k] < 0 || x > tv[k]) pos = k;
+                for (int k = p.nm - 1; k > pos; k--) {
+                    tv[k] = tv[k - 1];
+                    ts[k] = ts[k - 1];
+                }
+                if (pos < p.nm) {
+                    tv[pos] = x;
+                    ts[pos] = a;
+                }
+            }
+            for (int k = 0; k < p.nm; k++) {
+                topval[e * kNmMax + k] = tv[k];
+                topsym[e * kNmMax + k] = (uint16_t)ts[k];
+            }
+        }
+        __syncthreads();
+        // check nodes: one (check, output edge) task per thread, shared-memory chunk by chunk
+        const int tasks = M * p.dc_max;
+        for (int base = 0; base < tasks; base += p.ems_chunk) {
+            const int t = base + tid;
+            if (tid < p.ems_chunk && t < tasks) {
+                const int row = t / p.dc_max, dc = t - row * p.dc_max;
+                if (dc < p.cw[row]) ems_check_task(p, row, dc, v2c, topsym, topval, c2v, smemE + tid, p.ems_chunk);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        if (p.iters_out) p.iters_out[f] = it;
+        if (p.ok_out) p.ok_out[f] = ok;
+    }
+}
+
+// ---- TMM / layered TMM, NB/src/LDPC_Decoder.cpp:361-817 -----------------------------------------
+struct TmmShared {
+    float *vv, *dU, *Min1, *Min2, *I, *Ev;  // per group: [dc_max*q], [dc_max*q], [q] x4
+    int *MinCol, *Path, *Zn;                // [q], [2q], [dc_max + 1] (last = syndrome)
+};
+
+// the q threads of a group process check `row`; a = thread's symbol index.  Every thread of the CTA
+// calls this (same barriers); threads with act == false touch no memory.
+__device__ void tmm_check(const NbParams &p, int row, int a, bool act, const TmmShared &s, float *LLR, float *c2v,
+                          bool write_llr)
+{
+    const int q = p.q, w = act ? p.cw[row] : 0;
+    // v2c = LLR - c2v (:472-475 / :644)
+    for (int d = 0; d < w; d++) {
+        const int vn = p.c_vn[row * p.dc_max + d];
+        s.vv[d * q + a] = __fsub_rn(LLR[vn * q + a], c2v[((size_t)row * p.dc_max + d) * q + a]);
+    }
+    __syncthreads();
+    if (a < w) {  // d_TMM_Get_Zn :704-723 (first minimum)
+        float mn = INFINITY;
+        int me = 0;
+        const int h = p.c_gf[row * p.dc_max + a];
+        for (int x = 0; x < q; x++)
+            if (s.vv[a * q + x] < mn) {
+                mn = s.vv[a * q + x];
+                me = gmul(p, x, h);
+            }
+        s.Zn[a] = me;
+    }
+    __syncthreads();
+    if (act && a == 0) {
+        int syn = 0;
+        for (int d = 0; d < w; d++) syn ^= s.Zn[d];
+        s.Zn[p.dc_max] = syn;
+    }
+    for (int d = 0; d < w; d++) {  // d_TMM_Get_deltaU :725-743
+        const int hinv = __ldg(p.inv + p.c_gf[row * p.dc_max + d]);
+        const float mn = s.vv[d * q + gmul(p, hinv, s.Zn[d])];
+        s.dU[d * q + (a ^ s.Zn[d])] = __fsub_rn(s.vv[d * q + gmul(p, hinv, a)], mn);
+    }
+    __syncthreads();
+    if (act) {  // TMM_Get_Min :745-770
+        float m1 = INFINITY, m2 = INFINITY;
+        int col = 0;
+        for (int d = 0; d < w; d++) {
+            const float x = s.dU[d * q + a];
+            if (x < m1) {
+                m2 = m1;
+                m1 = x;
+                col = d;
+            } else if (x < m2)
+                m2 = x;
+        }
+        s.Min1[a] = m1;
+        s.Min2[a] = m2;
+        s.MinCol[a] = col;
+    }
+    __syncthreads();
+    if (act) {  // TMM_ConstructConf :772-817
+        float Ii = 0.0f, Ei = 0.0f;
+        int p0 = -1, p1 = -1;
+        if (a != 0) {
+            Ii = s.dU[s.MinCol[a] * q + a];
+            p0 = p1 = s.MinCol[a];
+            Ei = s.Min2[a];
+            for (int j = 0; j < q; j++) {
+                if (j == a) continue;
+                const int k = a ^ j;
+                const int cj = s.MinCol[j], ck = s.MinCol[k];
+                if (cj != ck) {
+                    const float d1 = s.dU[cj * q + j], d2 = s.dU[ck * q + k];
+                    if (d1 > d2 && d1 < Ii) {
+                        Ii = d1;
+                        p0 = cj;
+                        p1 = ck;
+                        Ei = s.Min1[a];
+                    } else if (d1 < d2 && d2 < Ii) {
+                        Ii = d2;
+                        p0 = cj;
+                        p1 = ck;
+                        Ei = s.Min1[a];
+                    }
+                }
+            }
+        }
+        s.I[a] = Ii;
+        s.Ev[a] = Ei;
+        s.Path[2 * a] = p0;
+        s.Path[2 * a + 1] = p1;
+    }
+    __syncthreads();
+    const int syn = act ? s.Zn[p.dc_max] : 0;
+    for (int d = 0; d < w; d++) {  // :496-521, thread = eta
+        const float l = (a == 0) ? 0.0f : ((d != s.Path[2 * a] && d != s.Path[2 * a + 1]) ? s.I[a] : s.Ev[a]);
+        const int hinv = __ldg(p.inv + p.c_gf[row * p.dc_max + d]);
+        const int beta = gmul(p, hinv, a ^ syn ^ s.Zn[d]);
+        const float m = (float)((double)l * 0.8);
+        c2v[((size_t)row * p.dc_max + d) * q + beta] = m;
+        if (write_llr) {  // layered: LLR = v2c + c2v_new (:684-689)
+            const int vn = p.c_vn[row * p.dc_max + d];
+            LLR[vn * q + beta] = __fadd_rn(s.vv[d * q + beta], m);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, float *c2v, uint16_t *sym, float *smem,
+                           int *s_fail, bool layered)
+{
+    const int q = p.q, N = p.N, M = p.M, tid = threadIdx.x, T = blockDim.x;
+    // init :363-402: LLR[0] = max_a L_ch, LLR[a] = max - L_ch[a-1]; c2v = 0
+    for (int col = tid; col < N; col += T) {
+        float mx = -INFINITY;
+        for (int a = 0; a < q - 1; a++) mx = fmaxf(mx, lch[col * (q - 1) + a]);
+        LLR[col * q] = mx;
+        for (int a = 1; a < q; a++) LLR[col * q + a] = __fsub_rn(mx, lch[col * (q - 1) + a - 1]);
+    }
+    for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 0.0f;
+    __syncthreads();
+    // thread groups of q threads: one check per group (layered: a single group keeps the row order)
+    const int groups = layered ? 1 : max(1, T / q);
+    const int g = tid / q, a = tid - g * q;
+    const size_t per_group = (size_t)2 * p.dc_max * q + 4 * q + q + 2 * q + p.dc_max + 1;
+    TmmShared s;
+    {
+        float *base = smem + (size_t)(g < groups ? g : 0) * per_group;
+        s.vv = base;
+        s.dU = s.vv + p.dc_max * q;
+        s.Min1 = s.dU + p.dc_max * q;
+        s.Min2 = s.Min1 + q;
+        s.I = s.Min2 + q;
+        s.Ev = s.I + q;
+        s.MinCol = reinterpret_cast<int *>(s.Ev + q);
+        s.Path = s.MinCol + q;
+        s.Zn = s.Path + 2 * q;
+    }
+    int it = 0, ok = 0;
+    while (it < p.maxit) {
+        it++;
+        if (!layered) {  // :423-434: LLR += sum_d c2v_d — cumulative over the iterations, as the reference
+            for (int i = tid; i < N * q; i += T) {
+                const int col = i / q, x = i - col * q;
+                float v = LLR[i];
+                for (int d = 0; d < p.vw[col]; d++)
+                    v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
+                LLR[i] = v;
+            }
+        }
+        if (tid == 0) *s_fail = 0;
+        __syncthreads();
+        for (int col = tid; col < N; col += T) {  // d_DecideLLRVector :92-105 (first minimum)
+            float mn = INFINITY;
+            int best = 0;
+            for (int x = 0; x < q; x++)
+                if (LLR[col * q + x] < mn) {
+                    mn = LLR[col * q + x];
+                    best = x;
+                }
+            sym[col] = (uint16_t)best;
+        }
+        __syncthreads();
+        syndrome(p, sym, s_fail);
+        __syncthreads();
+        if (*s_fail == 0) {
+            ok = 1;
+            it--;
+            break;
+        }
+        const int rounds = (M + groups - 1) / groups;
+        for (int r = 0; r < rounds; r++) {
+            const int row = r * groups + g;
+            tmm_check(p, row, a, g < groups && row < M, s, LLR, c2v, layered);
+        }
+    }
+    if (tid == 0) {
+        if (p.iters_out) p.iters_out[f] = it;
+        if (p.ok_out) p.ok_out[f] = ok;
+    }
+}
+
+__global__ void __launch_bounds__(kNbThreads)
+nb_decode_kernel(const __grid_constant__ NbParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_fail;
+    float *slot = p.scratch + (size_t)blockIdx.x * p.slot_floats;
+    const int q = p.q, N = p.N, M = p.M;
+    float *lch = slot;
+    float *LLR = lch + (size_t)N * (q - 1);
+    float *c2v = LLR + (size_t)N * q;
+    float *v2c = c2v + (size_t)M * p.dc_max * q;
+    float *topval = v2c + (size_t)N * p.dv_max * q;
+    uint16_t *topsym = reinterpret_cast<uint16_t *>(topval + (size_t)N * p.dv_max * kNmMax);
+    uint16_t *sym = topsym + (size_t)N * p.dv_max * kNmMax;
+    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+        demodulate(p, f, lch);
+        __syncthreads();
+        if (p.algo == NB_ALGO_EMS)
+            decode_ems(p, f, lch, LLR, c2v, v2c, topval, topsym, sym, smem, &s_fail);
+        else
+            decode_tmm(p, f, lch, LLR, c2v, sym, smem, &s_fail, p.algo == NB_ALGO_LAYERED_TMM);
+        __syncthreads();
+        for (int col = threadIdx.x; col < N; col += blockDim.x) p.out[(size_t)f * N + col] = sym[col];
+        __syncthreads();
+    }
+}
+
+static std::mutex g_nb_mu;
+
+static int nb_ensure_device(nb_ldpc_code *c)
+{
+    std::lock_guard<std::mutex> lk(g_nb_mu);
+    if (c->device >= 0) return LDPC_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return LDPC_ERR_NO_DEVICE;
+    }
+    int dev = 0, major = 0, sms = 0;
+    LDPC_CUDA_TRY(cudaGetDevice(&dev));
+    LDPC_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    LDPC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (major != 10) return LDPC_ERR_NO_DEVICE;
+#define UP(dst, vec, T)                                                                             \
+    LDPC_CUDA_TRY(cudaMalloc(&c->dst, (vec).size() * sizeof(T) + 16));                              \
+    LDPC_CUDA_TRY(cudaMemcpy(c->dst, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice));
+    UP(d_mul, c->mul, uint16_t)
+    UP(d_inv, c->inv, uint16_t)
+    UP(d_vw, c->vw, int)
+    UP(d_cw, c->cw, int)
+    UP(d_v_cn, c->v_cn, int)
+    UP(d_v_pos, c->v_pos, int)
+    UP(d_c_vn, c->c_vn, int)
+    UP(d_c_gf, c->c_gf, int)
+    UP(d_c_pos, c->c_pos, int)
+    UP(d_cre, c->cre, float)
+    UP(d_cim, c->cim, float)
+#undef UP
+    c->num_sms = sms;
+    c->device = dev;
+    return LDPC_OK;
+}
+
+}  // namespace ldpcb
+
+using namespace ldpcb;
+
+extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, uint16_t *hard_syms, int iters,
+                                    const nb_decode_opts_t *o)
+{
+    if (!cc || !in || !hard_syms || !o || iters <= 0) return LDPC_ERR_ARG;
+    if (o->struct_size != (int)sizeof(nb_decode_opts_t) || o->batch <= 0) return LDPC_ERR_ARG;
+    if (o->algo != NB_ALGO_EMS && o->algo != NB_ALGO_TMM && o->algo != NB_ALGO_LAYERED_TMM) return LDPC_ERR_ARG;
+    if (o->in_kind < 0 || o->in_kind > 2) return LDPC_ERR_ARG;
+    nb_ldpc_code *c = const_cast<nb_ldpc_code *>(cc);
+    if (o->algo == NB_ALGO_EMS && (o->ems_nm < 1 || o->ems_nm > kNmMax || o->ems_nc < 0)) return LDPC_ERR_UNSUPPORTED;
+    if (o->in_kind == NB_IN_BPSK && c->n_const != 2) return LDPC_ERR_ARG;
+    if (o->in_kind == NB_IN_QAM && c->n_const != c->q) return LDPC_ERR_ARG;
+    if (o->in_kind != NB_IN_SYMBOL_LLR && !(o->sigma > 0.0f)) return LDPC_ERR_ARG;
+    if (o->algo != NB_ALGO_EMS)
+        for (int g : c->c_gf)
+            if (g == 0) return LDPC_ERR_UNSUPPORTED;  // h^-1 does not exist (the reference exits with "Div 0 Error!")
+    if (o->in_kind == NB_IN_BPSK && (c->cre[0] != 1.0f || c->cre[1] != -1.0f)) return LDPC_ERR_UNSUPPORTED;
+    int rc = nb_ensure_device(c);
+    if (rc != LDPC_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
+    const int F = o->batch, q = c->q, N = c->N, M = c->M;
+    const bool host = o->mem_space == LDPC_MEM_HOST;
+    const size_t in_elems = (o->in_kind == NB_IN_SYMBOL_LLR) ? (size_t)N * (q - 1)
+                            : (o->in_kind == NB_IN_BPSK)     ? (size_t)N * c->p
+                                                             : (size_t)N * 2;
+    const size_t in_bytes = in_elems * F * sizeof(float), out_bytes = (size_t)F * N * sizeof(uint16_t);
+    // shared memory: EMS check chunk (transposed E) or TMM group arrays
+    size_t smem = 0;
+    int ems_chunk = 0;
+    if (o->algo == NB_ALGO_EMS) {
+        ems_chunk = kNbThreads;
+        while ((size_t)ems_chunk * q * sizeof(float) > 200 * 1024) ems_chunk /= 2;
+        smem = (size_t)ems_chunk * q * sizeof(float);
+    } else {
+        const int groups = (o->algo == NB_ALGO_LAYERED_TMM) ? 1 : (kNbThreads / q > 0 ? kNbThreads / q : 1);
+        if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA
+        smem = (size_t)groups * ((size_t)2 * c->dc_max * q + 7 * q + c->dc_max + 1) * sizeof(float);
+    }
+    if (smem > 227 * 1024) return LDPC_ERR_UNSUPPORTED;
+    LDPC_CUDA_TRY(cudaFuncSetAttribute(nb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nb_decode_kernel, kNbThreads, smem));
+    if (occ < 1) return LDPC_ERR_UNSUPPORTED;
+    int grid = c->num_sms * occ;
+    if (grid > F) grid = F;
+    size_t slot_floats = (size_t)N * (q - 1) + (size_t)N * q + (size_t)M * c->dc_max * q + (size_t)N * c->dv_max * q +
+                         (size_t)N * c->dv_max * kNmMax + ((size_t)N * c->dv_max * kNmMax + N) / 2 + 8;
+    slot_floats = (slot_floats + 63) & ~(size_t)63;
+    const size_t a256 = 255;
+    size_t need = (size_t)grid * slot_floats * sizeof(float);
+    const size_t o_in = need = (need + a256) & ~a256;
+    need += host ? ((in_bytes + a256) & ~a256) : 0;
+    const size_t o_out = need;
+    need += host ? ((out_bytes + a256) & ~a256) : 0;
+    const size_t o_it = need;
+    need += ((size_t)F * 4 + a256) & ~a256;
+    const size_t o_ok = need;
+    need += ((size_t)F * 4 + a256) & ~a256;
+    {
+        std::lock_guard<std::mutex> lk(g_nb_mu);
+        if (c->scratch_bytes < need) {
+            if (c->scratch) {
+                LDPC_CUDA_TRY(cudaDeviceSynchronize());
+                LDPC_CUDA_TRY(cudaFree(c->scratch));
+                c->scratch = nullptr;
+                c->scratch_bytes = 0;
+            }
+            LDPC_CUDA_TRY(cudaMalloc(&c->scratch, need));
+            c->scratch_bytes = need;
+        }
+    }
+    unsigned char *base = reinterpret_cast<unsigned char *>(c->scratch);
+    NbParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in;
+    p.out = hard_syms;
+    p.iters_out = o->iters_out;
+    p.ok_out = o->ok_out;
+    if (host) {
+        LDPC_CUDA_TRY(cudaMemcpyAsync(base + o_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+        p.in = base + o_in;
+        p.out = reinterpret_cast<uint16_t *>(base + o_out);
+        p.iters_out = reinterpret_cast<int *>(base + o_it);
+        p.ok_out = reinterpret_cast<int *>(base + o_ok);
+    }
+    p.scratch = reinterpret_cast<float *>(base);
+    p.slot_floats = slot_floats;
+    p.F = F;
+    p.N = N;
+    p.M = M;
+    p.q = q;
+    p.p = c->p;
+    p.dv_max = c->dv_max;
+    p.dc_max = c->dc_max;
+    p.n_const = c->n_const;
+    p.algo = o->algo;
+    p.in_kind = o->in_kind;
+    p.maxit = iters;
+    p.nm = o->ems_nm;
+    p.nc = o->ems_nc;
+    p.sigma = o->sigma;
+    p.ems_chunk = ems_chunk;
+    p.mul = c->d_mul;
+    p.inv = c->d_inv;
+    p.vw = c->d_vw;
+    p.cw = c->d_cw;
+    p.v_cn = c->d_v_cn;
+    p.v_pos = c->d_v_pos;
+    p.c_vn = c->d_c_vn;
+    p.c_gf = c->d_c_gf;
+    p.c_pos = c->d_c_pos;
+    p.cre = c->d_cre;
+    p.cim = c->d_cim;
+    nb_decode_kernel<<<grid, kNbThreads, smem, st>>>(p);
+    LDPC_CUDA_TRY(cudaGetLastError());
+    if (host) {
+        LDPC_CUDA_TRY(cudaMemcpyAsync(hard_syms, base + o_out, out_bytes, cudaMemcpyDeviceToHost, st));
+        if (o->iters_out)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->iters_out, base + o_it, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+        if (o->ok_out)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->ok_out, base + o_ok, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
+        LDPC_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return 1;
+}

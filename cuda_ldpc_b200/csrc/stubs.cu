@@ -4,9 +4,4 @@
 extern "C" int ldpc_awgn_bpsk(const ldpc_code_t *, float *, int, int, float, uint64_t, uint64_t, const uint8_t *, void *) { return LDPC_ERR_UNSUPPORTED; }
 extern "C" int ldpc_statistic(const ldpc_code_t *, const int *, const int *, int, int, const uint8_t *, int64_t *, void *) { return LDPC_ERR_UNSUPPORTED; }
 extern "C" int ldpc_encode(ldpc_code_t *, const uint8_t *, uint8_t *) { return LDPC_ERR_UNSUPPORTED; }
-extern "C" int nb_ldpc_load_code(const char *, const char *, const char *, int, nb_ldpc_code_t **) { return LDPC_ERR_UNSUPPORTED; }
-extern "C" void nb_ldpc_free_code(nb_ldpc_code_t *) {}
-extern "C" int nb_ldpc_code_info(const nb_ldpc_code_t *, nb_ldpc_code_info_t *) { return LDPC_ERR_UNSUPPORTED; }
-extern "C" int nb_ldpc_code_tables(const nb_ldpc_code_t *, uint16_t *, uint16_t *, int *, int *, int *) { return LDPC_ERR_UNSUPPORTED; }
-extern "C" void nb_decode_opts_default(nb_decode_opts_t *) {}
-extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *, const void *, uint16_t *, int, const nb_decode_opts_t *) { return LDPC_ERR_UNSUPPORTED; }
+
