@@ -67,8 +67,10 @@ def _load():
     L.ldpc_out_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.ldpc_awgn_bpsk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint64,
                                  C.c_void_p, C.c_void_p]
-    L.ldpc_statistic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]
+    L.ldpc_statistic.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ldpc_philox4x32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ldpc_philox4x32.restype = None
     L.ldpc_sigma.restype = C.c_float
     L.ldpc_sigma.argtypes = [C.c_int, C.c_float, C.c_float]
     L.ldpc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -133,11 +133,18 @@ typedef struct {
         num_Alarm_Frames;
 } ldpc_sim_counters_t;
 
-/* Replaces one call of Statistic (B/Simulation.cu:245-285) on device-resident decoder output
- * (LDPC_OUT_INT32_REF format, layout NF): accumulates into `counters_dev` (device, 6 x int64).
- * codeword_bits_dev NULL = all-zero.  length = leading bits compared (msgLen).              */
-int ldpc_statistic(const ldpc_code_t *code, const int *D_dev, const int *iters_dev, int batch, int length,
-                   const uint8_t *codeword_bits_dev, int64_t *counters_dev, void *stream);
+/* Replaces one call of Statistic (B/Simulation.cu:245-285) on device-resident decoder output:
+ * accumulates the six counters into `counters_dev` (device, ldpc_sim_counters_t layout).
+ * D_dev is in `out_format` (LDPC_OUT_INT32_REF or LDPC_OUT_U8, layout NF, or LDPC_OUT_BITPACK);
+ * ok_dev [F] = per-frame flag (NULL with INT32_REF: the flag row N is used).
+ * codeword_bits_dev NULL = all-zero codeword.  length = leading bits compared (msgLen).      */
+int ldpc_statistic(const ldpc_code_t *code, const void *D_dev, int out_format, const int *ok_dev,
+                   const int *iters_dev, int batch, int length, const uint8_t *codeword_bits_dev,
+                   int64_t *counters_dev, void *stream);
+
+/* The counter-based generator behind ldpc_awgn_bpsk (Philox4x32-10, Salmon et al. SC'11), exposed
+ * for known-answer tests: out[4] = philox(counter[4], key[2]).                                */
+void ldpc_philox4x32(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 
 /* B/main.cu:120-127 */
 float ldpc_sigma(int snrtype, float snr_db, float rate);
