@@ -34,8 +34,8 @@ EBN0_DB = 2.0
 # B_cw(it) = it*(2*E*w + 2*M*rec) + N*4 + N/8, int8: w = 1, rec = 4  -> 4 638 400 B at 10 it
 B_CW = ITERS * (2 * E * 1 + 2 * M * 4) + N * 4 + N // 8
 METRIC = "decoded info Gbit/s at fixed iters"
-WORKLOAD = ("binary QC-LDPC J15_L30_Z1280 (N=38400, K=19200), BPSK-AWGN Eb/N0 2.0 dB, layered min-sum "
-            "int8 state, 10 iterations fixed, no early exit")
+WORKLOAD = ("binary QC-LDPC J15_L30_Z1280 (N=38400, K=19200), BPSK-AWGN Eb/N0 2.0 dB, layered normalised "
+            "min-sum (x0.875), int8 state, 10 iterations fixed, no early exit")
 
 
 def measured_peaks():
@@ -107,7 +107,7 @@ def cpu_baseline_port(frames=4096):
     y = (1.0 + sigma * rng.standard_normal((N, frames))).astype(np.float32)
     D = np.zeros((N + 1) * frames, np.int32); it = np.zeros(frames, np.int32)
     t0 = time.perf_counter()
-    rc = lib.orc_layered_i8(J, L, Z, ip(H), y.ctypes.data, frames, ITERS, 8.0, 31, 0, 0, 0, D.ctypes.data,
+    rc = lib.orc_layered_i8(J, L, Z, ip(H), y.ctypes.data, frames, ITERS, 8.0, 31, 1, 3, 0, D.ctypes.data,
                             it.ctypes.data, None, None)
     dt = time.perf_counter() - t0
     assert rc == 0
@@ -287,8 +287,8 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=148 * 4 * 4)
     ap.add_argument("--msg-max", type=int, default=31)
     ap.add_argument("--llr-scale", type=float, default=8.0)
-    ap.add_argument("--beta-num", type=int, default=0)
-    ap.add_argument("--beta-shift", type=int, default=0)
+    ap.add_argument("--beta-num", type=int, default=1)
+    ap.add_argument("--beta-shift", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle timing (profiling runs)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the ncu capture")
     args = ap.parse_args()

@@ -177,6 +177,11 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
     // record words: [0,1] m1 (frames 01, 23)  [2,3] m2  [4,5] idx  [6 + h*SW + g] sign words
     const __half2 k1152 = __float2half2_rn(1152.0f), k1024 = __float2half2_rn(1024.0f);
     const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f);
+    __half2 dold[2];
+    if (!FIRST) {
+        dold[0] = __hsub2(u2h(rw[2]), u2h(rw[0]));
+        dold[1] = __hsub2(u2h(rw[3]), u2h(rw[1]));
+    }
     unsigned addr[DC];
     __half2 tp[2][DC];
     __half2 min1[2] = {amax, amax}, min2[2] = {amax, amax};
@@ -186,47 +191,32 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
     for (int h = 0; h < 2; h++)
 #pragma unroll
         for (int g = 0; g < SW; g++) sacc[h][g] = zero;
-    // pass 0: addresses, shared-memory loads and unpacking need nothing from the record, so they are
-    // issued first and cover the latency of the record load above
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
+            const __half2 kh = __float2half2_rn((float)k);
             const int2 e = p.tab[off + k];
             int col4 = i4 + e.y;
             col4 -= (col4 >= Z4) ? Z4 : 0;
             addr[k] = sbase + (unsigned)(e.x + col4);
             const unsigned wk = lds32(addr[k]);
-            tp[0][k] = u2h(prmt(wk, p.c64, 0x4140u));
-            tp[1][k] = u2h(prmt(wk, p.c64, 0x4342u));
-        }
-    }
-    // pass 1: t = APP - c2v_old, magnitudes, signs, min1 / min2 / first index
-    __half2 dold[2];
-    if (!FIRST) {
-        dold[0] = __hsub2(u2h(rw[2]), u2h(rw[0]));
-        dold[1] = __hsub2(u2h(rw[3]), u2h(rw[1]));
-    }
-#pragma unroll
-    for (int k = 0; k < DC; k++) {
-        if (EXACT || k < dc) {
-            const __half2 kh = __float2half2_rn((float)k);
             const int sh = 15 - sign_bit_pos(dc, k);  // brings edge k's sign bit to bit 15 of each lane
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                __half2 t1 = tp[h][k];
+                __half2 t1 = u2h(prmt(wk, p.c64, h ? 0x4342u : 0x4140u));
                 if (!FIRST) {
                     const __half2 mag = __hfma2(__heq2(u2h(rw[4 + h]), kh), dold[h], u2h(rw[h]));
                     const unsigned sg = (rw[6 + h * SW + k / kSignGroup] << sh) & 0x80008000u;
                     t1 = __hsub2(t1, u2h(h2u(mag) ^ sg));
-                    tp[h][k] = t1;
                 }
+                tp[h][k] = t1;
                 const __half2 tt = __hsub2(t1, k1152);
                 const __half2 ab = __hmin2(__habs2(tt), amax);
                 const __half2 neg = __hlt2(tt, zero);  // 1.0 where t < 0 (t is never -0)
                 sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
                 cnt[h] = __hadd2(cnt[h], neg);
-                const unsigned lt = __hlt2_mask(ab, min1[h]);
-                idx[h] = u2h(sel(lt, h2u(kh), h2u(idx[h])));
+                const __half2 lt = __hlt2(ab, min1[h]);
+                idx[h] = __hfma2(lt, __hsub2(kh, idx[h]), idx[h]);
                 min2[h] = __hmin2(min2[h], __hmax2(min1[h], ab));
                 min1[h] = __hmin2(min1[h], ab);
             }
@@ -478,6 +468,11 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         }
         if (tid == 0) s_fail = 0u;
         __syncthreads();
+        // pull the channel values of this CTA's next group towards L2 while this group is decoded
+        if (g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 && p.layout == LDPC_LAYOUT_NF) {
+            const float *y = reinterpret_cast<const float *>(p.llr) + 4 * (size_t)(g + gridDim.x);
+            for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
+        }
 
         unsigned running = valid;  // frames not yet latched
         int it = 0;
