@@ -147,9 +147,12 @@ class LdpcCode:
             a = a.astype(np.float32)
         dt = _NP_DTYPES[a.dtype]
         nbytes = self.out_bytes(F, out_format)
-        outb = np.zeros(nbytes, np.uint8)
-        it = np.zeros(F, np.int32)
-        ok = np.zeros(F, np.int32)
+        # caller-provided (e.g. pinned) result buffers avoid a pageable D2H copy per call
+        outb = np.zeros(nbytes, np.uint8) if out is None else out.view(np.uint8).reshape(-1)
+        it = np.zeros(F, np.int32) if iters_out is None else iters_out
+        ok = np.zeros(F, np.int32) if ok_out is None else ok_out
+        if outb.size != nbytes or it.size != F or ok.size != F:
+            raise ValueError("result buffers have the wrong size")
         app = msgs = None
         if debug:
             if schedule == SCHED_LAYERED:

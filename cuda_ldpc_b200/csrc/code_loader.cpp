@@ -124,6 +124,7 @@ extern "C" int ldpc_load_code(const char *path, int J, int L, int Z, ldpc_code_t
     c->Wv.assign(L + 1, 0);
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    c->pipe_stream[0] = c->pipe_stream[1] = nullptr;
     c->enc_state = 0;
     memset(&c->lt, 0, sizeof(c->lt));
     memset(&c->ct, 0, sizeof(c->ct));
@@ -187,6 +188,8 @@ extern "C" void ldpc_free_code(ldpc_code_t *code)
 {
     if (!code) return;
     if (code->scratch) cudaFree(code->scratch);
+    for (int i = 0; i < 2; i++)
+        if (code->pipe_stream[i]) cudaStreamDestroy(code->pipe_stream[i]);
     delete code;
 }
 

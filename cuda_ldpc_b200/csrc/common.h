@@ -61,6 +61,8 @@ struct ldpc_code {
     // scratch arena (device), grown on demand under `mu`
     void *scratch;
     size_t scratch_bytes;
+    // two internal streams for the chunked host path (H2D of chunk k+1 under the decode of chunk k)
+    cudaStream_t pipe_stream[2];
     // encoder cache (host): parity-part inverse, built lazily
     std::vector<uint32_t> enc_cache;
     int enc_state;  // 0 = not built, 1 = ok, -1 = singular

@@ -180,3 +180,25 @@ def test_device_path_and_large_batch_properties(oracle):
     yo = y[:, :8].cpu().numpy()
     Do, its, _, _ = orc_i8(oracle, oc, yo, 10, 2, amax=31)
     assert (Do[: code.N] == D[:, :8]).all() and (its == r.iters.cpu().numpy()[:8]).all()
+
+
+@pytest.mark.parametrize("layout,fmt", [(m.LAYOUT_NF, m.OUT_BITPACK), (m.LAYOUT_NF, m.OUT_INT32_REF),
+                                        (m.LAYOUT_FN, m.OUT_U8), (m.LAYOUT_NF, m.OUT_U8)])
+def test_chunked_host_path_equals_device_path(oracle, layout, fmt):
+    """Large host batches are decoded in chunks on two internal streams (copy/compute overlap): same
+    bits, iteration counts and flags as one device-resident call, for every layout / output format."""
+    import torch
+    code, _ = load(oracle, "C1")
+    F = 3001  # not a multiple of the chunk (4*SMs*2) nor of 4
+    y = noisy(oracle, code.N, 64, 2.8)
+    y = np.tile(y, (1, 47))[:, :F] * (1.0 + 0.01 * np.arange(F, dtype=np.float32)[None, :] / F)
+    yy = np.ascontiguousarray(y if layout == m.LAYOUT_NF else y.T)
+    kw = dict(schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=fmt, layout=layout, msg_max=31,
+              beta_num=1, beta_shift=3)
+    rh = code.decode(yy, 10, **kw)
+    rd = code.decode(torch.as_tensor(yy, device="cuda"), 10, **kw)
+    torch.cuda.synchronize()
+    got = rd.D.cpu().numpy()
+    assert (rh.D == (got.view(np.uint32) if fmt == m.OUT_BITPACK else got)).all()
+    assert (rh.iters == rd.iters.cpu().numpy()).all() and (rh.ok == rd.ok.cpu().numpy()).all()
+    assert rh.launches == 3 and rd.launches == 1
