@@ -82,6 +82,12 @@ def _load():
     L.nb_decode_opts_default.argtypes = [C.POINTER(NbDecodeOpts)]
     L.nb_decode_opts_default.restype = None
     L.nb_ldpc_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(NbDecodeOpts)]
+    L.nb_ldpc_sigma.restype = C.c_float
+    L.nb_ldpc_sigma.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+    L.nb_ldpc_modulate_awgn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_uint64,
+                                        C.c_void_p, C.c_void_p]
+    L.nb_ldpc_statistic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]
     return L
 
 

@@ -446,7 +446,7 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
 
 static std::mutex g_nb_mu;
 
-static int nb_ensure_device(nb_ldpc_code *c)
+int nb_upload_tables(nb_ldpc_code *c)
 {
     std::lock_guard<std::mutex> lk(g_nb_mu);
     if (c->device >= 0) return LDPC_OK;
@@ -500,7 +500,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
         for (int g : c->c_gf)
             if (g == 0) return LDPC_ERR_UNSUPPORTED;  // h^-1 does not exist (the reference exits with "Div 0 Error!")
     if (o->in_kind == NB_IN_BPSK && (c->cre[0] != 1.0f || c->cre[1] != -1.0f)) return LDPC_ERR_UNSUPPORTED;
-    int rc = nb_ensure_device(c);
+    int rc = nb_upload_tables(c);
     if (rc != LDPC_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
     const int F = o->batch, q = c->q, N = c->N, M = c->M;

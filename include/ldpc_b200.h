@@ -207,6 +207,27 @@ void nb_decode_opts_default(nb_decode_opts_t *opts);
 int nb_ldpc_decode_batch(const nb_ldpc_code_t *code, const void *in, uint16_t *hard_syms, int iters,
                          const nb_decode_opts_t *opts);
 
+/* NB/src/main.cu:221-228: sigma from SNR; bits per channel use = log2(n_qam), rate = (N-M)/N.
+ * snrtype 0 = Eb/N0, 1 = Es/N0.  n_qam <= 0: the loaded constellation's size.                 */
+float nb_ldpc_sigma(const nb_ldpc_code_t *code, int snrtype, float snr_db, int n_qam);
+
+/* On-device transmitter + channel for the non-binary simulator: replaces BitToSym / Modulate
+ * (NB/src/LDPC_Encoder.cpp:6-37, NB/src/main.cu:190-212) and the complex AWGNChannel_CPU
+ * (NB/src/LDPC_Encoder.cpp:41-68).  codeword_syms_dev: uint16 [N] broadcast to all frames (NULL =
+ * all-zero).  BPSK constellation: out = float [F][N*p] (real parts; the reference also draws and then
+ * ignores an imaginary part); otherwise out = float [F][N][2].  Noise: Philox4x32-10 keyed by
+ * (seed, global frame index, sample index).  Output feeds nb_ldpc_decode_batch (NB_IN_BPSK / NB_IN_QAM). */
+int nb_ldpc_modulate_awgn(const nb_ldpc_code_t *code, float *out_dev, int batch, float sigma, uint64_t seed,
+                          uint64_t first_frame, const uint16_t *codeword_syms_dev, void *stream);
+
+/* Replaces NB Statistic (NB/src/Simulation.cpp:256-311) on device-resident decoder output
+ * hard_syms_dev uint16 [F][N]: counters_dev (ldpc_sim_counters_t layout) accumulates frames, error
+ * frames (any symbol wrong), symbol errors over ALL N symbols (what the reference prints as "BER"),
+ * iterations, false frames (wrong but syndrome ok) and alarm frames (right but flagged).      */
+int nb_ldpc_statistic(const nb_ldpc_code_t *code, const uint16_t *hard_syms_dev, const int *iters_dev,
+                      const int *ok_dev, int batch, const uint16_t *codeword_syms_dev, int64_t *counters_dev,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,3 +122,76 @@ def test_device_path_and_errors(gf_dir, meta):
     with pytest.raises(m.LdpcError) as e:
         raw.decode(np.zeros((1, raw.N * 2), np.float32), 5, algo=m.ALGO_TMM, in_kind=m.IN_QAM, sigma=0.2)
     assert e.value.code == -6
+
+
+def test_nb_channel_statistic_and_cli(nb_oracle, gf_dir, meta):
+    """Device transmitter + channel (BPSK and 64-QAM), statistic kernel and the nb_ldpc_sim driver:
+    noise statistics, shard independence, counter formulas of NB Statistic, and an SER / FER at 3 dB
+    (BDS, layered TMM) consistent with the oracle decoding an independent sample."""
+    import subprocess
+    import torch
+    from conftest import ROOT
+    cfg = meta["configs"]["BDS"]
+    mt, gf, cs = paths(cfg, gf_dir)
+    code = m.NbLdpcCode(mt, gf, cs)
+    cw = np.array(meta["CodeWord_sym_test"], np.uint16)
+    cwd = torch.as_tensor(cw.astype(np.int16), device="cuda")
+    F, L = 1024, code.N * code.p
+    st = torch.cuda.current_stream().cuda_stream
+    sigma = m.lib.nb_ldpc_sigma(code._h, 0, 3.0, 0)
+    h = orc_load(nb_oracle, cfg, gf_dir, 0)
+    assert sigma == pytest.approx(nb_oracle.nb_orc_sigma(h, 0, 3.0), rel=1e-7)
+
+    def gen(F, first):
+        x = torch.empty(F * L, dtype=torch.float32, device="cuda")
+        assert m.lib.nb_ldpc_modulate_awgn(code._h, x.data_ptr(), F, sigma, 173, first, cwd.data_ptr(), st) >= 0
+        torch.cuda.synchronize()
+        return x.view(F, L)
+    x = gen(F, 0)
+    bits = ((cw[:, None] >> np.arange(code.p)) & 1).reshape(-1)
+    n = ((x.cpu().numpy() - (1.0 - 2.0 * bits)[None]) / sigma)
+    assert abs(n.mean()) < 0.01 and abs(n.var() - 1) < 0.01 and abs((n ** 4).mean() - 3) < 0.1
+    assert (torch.cat([gen(300, 0), gen(724, 300)]) == x).all()
+    out, it, ok = code.decode(x, 20, algo=m.ALGO_LAYERED_TMM, in_kind=m.IN_BPSK, sigma=sigma)
+    cnt = torch.zeros(6, dtype=torch.int64, device="cuda")
+    assert m.lib.nb_ldpc_statistic(code._h, out.data_ptr(), it.data_ptr(), ok.data_ptr(), F, cwd.data_ptr(),
+                                   cnt.data_ptr(), st) >= 0
+    o, i_, k_ = out.cpu().numpy().astype(np.int32), it.cpu().numpy(), ok.cpu().numpy()
+    err = (o != cw[None].astype(np.int32)).sum(1)
+    want = [F, (err != 0).sum(), err.sum(), i_.sum(), ((err != 0) & (k_ == 1)).sum(), ((err == 0) & (k_ == 0)).sum()]
+    assert cnt.cpu().numpy().tolist() == [int(v) for v in want]
+    # oracle FER on an independent sample of the same channel
+    Fo = 256
+    lch = np.zeros((Fo, code.N * (code.q - 1)), np.float32)
+    tx = np.zeros(2 * L, np.float32)
+    sym = cw.astype(np.int32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    seed = np.array([7, 11, 13], np.int32)
+    rx = np.zeros(2 * L, np.float32)
+    for f in range(Fo):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rx.ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rx.ctypes.data, lch[f].ctypes.data)
+    oo = np.zeros((Fo, code.N), np.int32); oi = np.zeros(Fo, np.int32); ok_o = np.zeros(Fo, np.int32)
+    nb_oracle.nb_orc_decode_batch(h, 3, 0, lch.ctypes.data, Fo, 20, 2, 2, oo.ctypes.data, oi.ctypes.data, ok_o.ctypes.data)
+    fer_o = ((oo != sym[None]).sum(1) != 0).mean()
+    fer_e = want[1] / F
+    se = np.sqrt(max(fer_o * (1 - fer_o), 1e-3) / Fo + max(fer_e * (1 - fer_e), 1e-3) / F)
+    assert abs(fer_e - fer_o) < 4 * se + 0.01, (fer_e, fer_o)
+    # 64-QAM transmitter: mean of the received points = the constellation point of the sent symbol
+    c4 = meta["configs"]["C4"]
+    mt4, gf4, cs4 = paths(c4, gf_dir)
+    qam = m.NbLdpcCode(mt4, gf4, cs4, coef_is_exponent=True)
+    y = torch.empty(2048 * qam.N * 2, dtype=torch.float32, device="cuda")
+    assert m.lib.nb_ldpc_modulate_awgn(qam._h, y.data_ptr(), 2048, 0.1, 5, 0, None, st) >= 0
+    pts = np.loadtxt(cs4, usecols=(3, 5))
+    mean = y.view(2048, qam.N, 2).mean((0, 1)).cpu().numpy()
+    assert np.allclose(mean, pts[0], atol=2e-3)
+    # driver
+    exe = os.path.join(ROOT, "cuda_ldpc_b200", "nb_ldpc_sim")
+    r = subprocess.run([exe, "--matrix", mt, "--gf", gf, "--constellation", cs, "--algo", "ltmm", "--snr", "2.0", "3.0", "1.0",
+                        "--batch", "1024", "--max-frames", "8192", "--codeword", os.path.join(GOLDEN, "nb_BDS_codeword.txt")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rows = [l.split() for l in r.stdout.splitlines() if l.startswith(" 2.0") or l.startswith(" 3.0")]
+    assert len(rows) == 2 and float(rows[0][3]) > float(rows[1][3]) > 0
+    assert abs(float(rows[1][3]) - fer_e) < 0.02  # same point (3 dB), same decoder
