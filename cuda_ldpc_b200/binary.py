@@ -116,9 +116,12 @@ class LdpcCode:
                 ok_out = torch.empty(F, dtype=torch.int32, device=dev)
             app = msgs = None
             if debug:
-                if schedule == SCHED_LAYERED:
-                    app = torch.zeros(N * F * (1 if msg_dtype == DTYPE_INT8 else 4), dtype=torch.uint8, device=dev)
+                if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
+                    app = torch.zeros(N * F, dtype=torch.uint8, device=dev)
                     msgs = torch.zeros(self.M * 4 * F, dtype=torch.int32, device=dev)
+                elif schedule == SCHED_LAYERED:
+                    app = torch.zeros(N * F, dtype=torch.float32, device=dev)
+                    msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.float32, device=dev)
                 else:
                     msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.float32, device=dev)
             if stream is None:
@@ -138,8 +141,8 @@ class LdpcCode:
                 D = out.view(N, F) if layout == LAYOUT_NF else out.view(F, N)
             else:
                 D = out.view(torch.int32).view(F, (N + 31) // 32)
-            if app is not None and msg_dtype == DTYPE_INT8:
-                app = app.view(torch.int8).view(N, F)
+            if app is not None:
+                app = app.view(torch.int8).view(N, F) if msg_dtype == DTYPE_INT8 else app.view(N, F)
             return DecodeResult(D, iters_out, ok_out, rc, app, msgs)
         # ---- host path
         a = np.ascontiguousarray(llr)
@@ -155,9 +158,12 @@ class LdpcCode:
             raise ValueError("result buffers have the wrong size")
         app = msgs = None
         if debug:
-            if schedule == SCHED_LAYERED:
-                app = np.zeros(N * F, np.int8 if msg_dtype == DTYPE_INT8 else np.float32)
+            if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
+                app = np.zeros(N * F, np.int8)
                 msgs = np.zeros(self.M * 4 * F, np.uint32)
+            elif schedule == SCHED_LAYERED:
+                app = np.zeros(N * F, np.float32)
+                msgs = np.zeros(self.M * self.dc_max * F, np.float32)
             else:
                 msgs = np.zeros(self.M * self.dc_max * F, np.float32)
         o = self.make_opts(F, layout=layout, llr_dtype=dt, mem_space=MEM_HOST, schedule=schedule, msg_dtype=msg_dtype,

@@ -210,11 +210,14 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     if (o->layout != LDPC_LAYOUT_NF && o->layout != LDPC_LAYOUT_FN) return LDPC_ERR_ARG;
     if (o->llr_dtype < 0 || o->llr_dtype > 2 || o->out_format < 0 || o->out_format > 2) return LDPC_ERR_ARG;
     if (o->early_exit < 0 || o->early_exit > 2) return LDPC_ERR_ARG;
-    const bool flooding = (o->schedule == LDPC_SCHED_FLOODING);
-    if (!flooding && o->schedule != LDPC_SCHED_LAYERED) return LDPC_ERR_ARG;
+    if (o->schedule != LDPC_SCHED_FLOODING && o->schedule != LDPC_SCHED_LAYERED) return LDPC_ERR_ARG;
+    // "flooding" below = the streaming fp32 paths (messages in HBM, hard bits emitted by a conversion
+    // kernel): flooding fp32 and layered fp32.  The layered int8 path has its own I/O inside the kernel.
+    const bool layered_f32 = (o->schedule == LDPC_SCHED_LAYERED && o->msg_dtype == LDPC_DTYPE_FP32);
+    const bool flooding = (o->schedule == LDPC_SCHED_FLOODING) || layered_f32;
     if (flooding && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
-    if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8 && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
-    if (!flooding && o->early_exit == LDPC_EXIT_GENIE) return LDPC_ERR_UNSUPPORTED;
+    if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8) return LDPC_ERR_UNSUPPORTED;
+    if (o->schedule == LDPC_SCHED_LAYERED && o->early_exit == LDPC_EXIT_GENIE) return LDPC_ERR_UNSUPPORTED;
     int rc = ensure_device(c);
     if (rc != LDPC_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
@@ -228,7 +231,8 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     }
     const size_t in_bytes = (size_t)c->N * F * dtype_bytes(o->llr_dtype);
     const size_t out_bytes = ldpc_out_bytes(c, F, o->out_format);
-    const size_t dbg_app_bytes = o->debug_app ? (size_t)c->N * F * (flooding ? 0 : (o->msg_dtype == LDPC_DTYPE_INT8 ? 1 : 4)) : 0;
+    const size_t dbg_app_bytes =
+        o->debug_app ? (size_t)c->N * F * (layered_f32 ? 4 : (flooding ? 0 : 1)) : 0;
     const size_t dbg_msg_bytes =
         o->debug_msgs ? (flooding ? (size_t)c->M * c->dc_max * F * 4 : (size_t)c->M * 4 * F * 4) : 0;
 
@@ -240,13 +244,14 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     const size_t o_ok = need;      need += align_up((size_t)F * 4);
     const size_t o_dapp = need;    need += host ? align_up(dbg_app_bytes) : 0;
     const size_t o_dmsg = need;    need += (host && !flooding) ? align_up(dbg_msg_bytes) : 0;
-    size_t o_y = 0, o_msgs = 0, o_hard = 0, o_flags = 0;
+    size_t o_y = 0, o_msgs = 0, o_hard = 0, o_flags = 0, o_app = 0;
     const bool need_conv = flooding && (o->llr_dtype != LDPC_DTYPE_FP32 || o->layout != LDPC_LAYOUT_NF);
     if (flooding) {
         o_y = need;     need += need_conv ? align_up((size_t)c->N * F * 4) : 0;
         o_msgs = need;  need += align_up((size_t)c->M * c->dc_max * F * 4);
         o_hard = need;  need += align_up((size_t)c->N * F);
         o_flags = need; need += align_up((size_t)(2 * F + 1) * 4);
+        o_app = need;   need += layered_f32 ? align_up((size_t)c->N * F * 4) : 0;
     }
     const size_t o_layer = need;  // the layered kernel sizes its own slice behind this offset
     unsigned char *base = nullptr;
@@ -286,9 +291,16 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         }
         float *msgs = reinterpret_cast<float *>(base + o_msgs);
         unsigned char *hard = base + o_hard;
-        rc = launch_flooding_fp32(c, y, F, iters, o->early_exit, hard, d_it, d_ok, msgs,
-                                  reinterpret_cast<int *>(base + o_flags), st, &launches);
+        if (layered_f32)
+            rc = launch_layered_f32_nf(c, y, F, iters, o->early_exit, o->alpha, reinterpret_cast<float *>(base + o_app),
+                                       msgs, hard, d_it, d_ok, reinterpret_cast<int *>(base + o_flags), st, &launches);
+        else
+            rc = launch_flooding_fp32(c, y, F, iters, o->early_exit, hard, d_it, d_ok, msgs,
+                                      reinterpret_cast<int *>(base + o_flags), st, &launches);
         if (rc != LDPC_OK) return rc;
+        if (layered_f32 && o->debug_app)
+            LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_app, base + o_app, dbg_app_bytes,
+                                          host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
         const long long n = (o->out_format == LDPC_OUT_BITPACK) ? (long long)((c->N + 31) / 32) * F
                                                                 : (long long)(c->N + 1) * F;
         emit_hard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hard, d_ok, d_out, o->out_format, o->layout,
@@ -319,10 +331,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         a.dbg_rec = d_dmsg;
         a.scratch = base + o_layer;
         a.scratch_bytes = layered_extra;
-        if (o->msg_dtype == LDPC_DTYPE_INT8)
-            rc = launch_layered_i8(c, a, st, &launches);
-        else
-            rc = launch_layered_fp32(c, a, st, &launches);
+        rc = launch_layered_i8(c, a, st, &launches);
         if (rc != LDPC_OK) return rc;
         if (host && o->debug_msgs)
             LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_msgs, d_dmsg, dbg_msg_bytes, cudaMemcpyDeviceToHost, st));
@@ -332,7 +341,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         if (o->iters_out)
             LDPC_CUDA_TRY(cudaMemcpyAsync(o->iters_out, d_it, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
         if (o->ok_out) LDPC_CUDA_TRY(cudaMemcpyAsync(o->ok_out, d_ok, (size_t)F * 4, cudaMemcpyDeviceToHost, st));
-        if (o->debug_app && dbg_app_bytes)
+        if (o->debug_app && dbg_app_bytes && !flooding)
             LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_app, d_dapp, dbg_app_bytes, cudaMemcpyDeviceToHost, st));
         LDPC_CUDA_TRY(cudaStreamSynchronize(st));
     }

@@ -131,7 +131,7 @@ flood_cn_kernel(const __grid_constant__ LayerTables lt, float *__restrict__ msgs
 }
 
 // bad[f] |= 1 if any check of frame f has odd parity on hard[N][F]
-__global__ void __launch_bounds__(256)
+__global__ void
 syndrome_nf_kernel(const __grid_constant__ LayerTables lt, const unsigned char *__restrict__ hard,
                    int *__restrict__ bad, int M, int Z, int F)
 {
@@ -159,7 +159,7 @@ genie_nf_kernel(const unsigned char *__restrict__ hard, int *__restrict__ bad, i
 }
 
 // per-frame bookkeeping after iteration `it`; counter[0] += frames still running
-__global__ void __launch_bounds__(256)
+__global__ void
 flood_finalize_kernel(const int *__restrict__ bad, int *__restrict__ done, int *__restrict__ iters,
                       int *__restrict__ ok, int *__restrict__ counter, int it, int F, int latch)
 {

@@ -634,6 +634,5 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     return rc;
 }
 
-int launch_layered_fp32(const ldpc_code *, const LayeredArgs &, cudaStream_t, int *) { return LDPC_ERR_UNSUPPORTED; }
 
 }  // namespace ldpcb

@@ -14,6 +14,11 @@ DATA = os.path.join(ROOT, "cuda_ldpc_b200", "data")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product library is built in-tree (sm_100a cross-compiles without a GPU); build it if a fresh
+    # checkout has not run __graft_entry__.build() yet
+    lib = os.path.join(ROOT, "cuda_ldpc_b200", "libldpc_b200.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "cuda_ldpc_b200", "csrc")])
 
 
 def ip(a):

@@ -202,3 +202,50 @@ def test_chunked_host_path_equals_device_path(oracle, layout, fmt):
     assert (rh.D == (got.view(np.uint32) if fmt == m.OUT_BITPACK else got)).all()
     assert (rh.iters == rd.iters.cpu().numpy()).all() and (rh.ok == rd.ok.cpu().numpy()).all()
     assert rh.launches == 3 and rd.launches == 1
+
+
+ALL_FILES = sorted(f for f in os.listdir(BL) if f.endswith(".txt"))
+
+
+@pytest.mark.parametrize("fname", ALL_FILES)
+def test_every_shipped_code_both_schedules(oracle, fname):
+    """All 18 H files of the reference (dc 4..24, dv 2..15, Z 64..1280): flooding fp32 and layered int8
+    bit-exact against the oracle on a small seeded batch (exercises every degree bucket, the exact-degree
+    instances and the out-of-line generic path)."""
+    import re
+    geo = (12, 69, 256) if fname == "PON_LDPC.txt" else tuple(int(x) for x in re.match(r"J(\d+)_L(\d+)_Z(\d+)", fname).groups())
+    path = os.path.join(BL, fname)
+    code, oc = m.LdpcCode(path, *geo), OracleCode(oracle, path, *geo)
+    F = 8 if code.N > 20000 else 12
+    snr = 10 * np.log10(1.0 / (2 * code.rate)) + 3.0 + (1.5 if code.rate > 0.7 else 0.0)  # near the waterfall (Es/N0)
+    y = noisy(oracle, code.N, F, snr)
+    r = code.decode(y, 6, schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, debug=True, msg_max=31, beta_num=1,
+                    beta_shift=3)
+    D, its, app, rec = orc_i8(oracle, oc, y, 6, 2, amax=31, bnum=1, bshift=3)
+    assert (r.D == D).all() and (r.iters == its).all() and (r.app == app).all() and (r.msgs == rec).all(), fname
+    r = code.decode(y, 4, debug=True)
+    D, it, rq = orc_flood(oracle, oc, y, 4, 0)
+    assert (r.D == D).all() and (r.msgs.view(np.uint32) == rq.view(np.uint32)).all(), fname
+
+
+def orc_l32(oracle, oc, y, maxit, mode, alpha=1.0):
+    N, F = y.shape
+    D = np.zeros((N + 1) * F, np.int32)
+    it = np.zeros(F, np.int32)
+    app = np.zeros(N * F, np.float32)
+    assert oracle.orc_layered_fp32(oc.J, oc.L, oc.Z, ip(oc.H), fp(np.ascontiguousarray(y)), F, maxit, alpha, mode,
+                                   ip(D), ip(it), app.ctypes.data) == 0
+    return D.reshape(N + 1, F), it, app.reshape(N, F)
+
+
+@pytest.mark.parametrize("key,F,snr,alpha,mode", [("C1", 32, 2.8, 1.0, 0), ("C1", 21, 2.8, 0.8125, 2),
+                                                  ("C3", 8, 3.2, 0.875, 2), ("C2", 8, 0.0, 1.0, 2), ("J10", 8, 4.0, 0.75, 0)])
+def test_layered_fp32_bit_exact_vs_oracle(oracle, key, F, snr, alpha, mode):
+    """The float twin of the throughput mode: every APP value (bit pattern), hard bit, iteration count
+    and flag equals the oracle's layered fp32 (same operation order, no FMA contraction)."""
+    code, oc = load(oracle, key)
+    y = noisy(oracle, code.N, F, snr)
+    r = code.decode(y, 8, schedule=m.SCHED_LAYERED, msg_dtype=m.DTYPE_FP32, early_exit=mode, alpha=alpha, debug=True)
+    D, it, app = orc_l32(oracle, oc, y, 8, mode, alpha)
+    assert (r.iters == it).all() and (r.D == D).all()
+    assert (r.app.view(np.uint32) == app.view(np.uint32)).all()
