@@ -11,6 +11,6 @@ from .binary import (  # noqa: F401
     EXIT_NONE, EXIT_GENIE, EXIT_SYNDROME, OUT_INT32_REF, OUT_U8, OUT_BITPACK,
 )
 
-from .nonbinary import NbLdpcCode, ALGO_EMS, ALGO_TMM, ALGO_LAYERED_TMM, IN_SYMBOL_LLR, IN_BPSK, IN_QAM  # noqa: F401,E402
+from .nonbinary import NbLdpcCode, ALGO_EMS, ALGO_TMM, ALGO_LAYERED_TMM, ALGO_FFT_BP, IN_SYMBOL_LLR, IN_BPSK, IN_QAM  # noqa: F401,E402
 
 DATA_DIR = __import__("os").path.join(__import__("os").path.dirname(__file__), "data")

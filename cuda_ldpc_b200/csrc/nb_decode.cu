@@ -417,6 +417,137 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
     }
 }
 
+
+// ---- FFT-BP (not in the reference; rules = oracle/nb_oracle.c decode_fftbp) ------------------------
+// Check node in the Walsh-Hadamard domain: GF(2^p) addition is XOR, so the convolution of the
+// (permuted) input distributions is a pointwise product of their WHTs.  q threads per check; the
+// butterflies run in shared memory in the oracle's pairing.  A dense [dc x q] x H_q contraction on the
+// tensor cores is the alternative the north star mentions; at q <= 256 and dc <= 12 the transform is
+// 8 butterfly stages on 12 KB and is not the bottleneck of this path.
+__device__ __forceinline__ void wht_stage_all(float *F, int q, int w, int a)
+{
+    for (int len = 1; len < q; len <<= 1) {
+        if (a < q / 2) {
+            const int j = (a / len) * 2 * len + (a % len);
+            for (int d = 0; d < w; d++) {
+                const float u = F[d * q + j], v = F[d * q + j + len];
+                F[d * q + j] = __fadd_rn(u, v);
+                F[d * q + j + len] = __fsub_rn(u, v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, float *c2v, float *v2c, uint16_t *sym,
+                             float *smem, int *s_fail)
+{
+    const int q = p.q, N = p.N, M = p.M, tid = threadIdx.x, T = blockDim.x;
+    for (int col = tid; col < N; col += T) {
+        float mx = 0.0f;
+        for (int a = 0; a < q - 1; a++) mx = fmaxf(mx, lch[col * (q - 1) + a]);
+        float s = 0.0f;
+        for (int a = 0; a < q; a++) {
+            const float v = expf(__fsub_rn(a ? lch[col * (q - 1) + a - 1] : 0.0f, mx));
+            pch[col * q + a] = v;
+            s = __fadd_rn(s, v);
+        }
+        for (int a = 0; a < q; a++) pch[col * q + a] = __fdiv_rn(pch[col * q + a], s);
+    }
+    for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 1.0f;
+    __syncthreads();
+    const int groups = max(1, T / q), g = tid / q, a = tid - g * q;
+    const size_t per_group = (size_t)(p.dc_max + 2) * q + 4;
+    float *F = smem + (size_t)(g < groups ? g : 0) * per_group, *G = F + p.dc_max * q, *tmp = G + q, *ssum = tmp + q;
+    int it = 0, ok = 0;
+    while (it < p.maxit) {
+        it++;
+        if (tid == 0) *s_fail = 0;
+        for (int col = tid; col < N; col += T) {
+            float best = -1.0f;
+            int bi = 0;
+            for (int x = 0; x < q; x++) {
+                float v = pch[col * q + x];
+                for (int d = 0; d < p.vw[col]; d++)
+                    v = __fmul_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
+                if (v > best) {
+                    best = v;
+                    bi = x;
+                }
+            }
+            sym[col] = (uint16_t)bi;
+        }
+        __syncthreads();
+        syndrome(p, sym, s_fail);
+        __syncthreads();
+        if (*s_fail == 0) {
+            ok = 1;
+            it--;
+            break;
+        }
+        for (int e = tid; e < N * p.dv_max; e += T) {
+            const int col = e / p.dv_max, d = e - col * p.dv_max;
+            if (d >= p.vw[col]) continue;
+            float *v = v2c + (size_t)e * q;
+            float s = 0.0f;
+            for (int x = 0; x < q; x++) {
+                float t = pch[col * q + x];
+                for (int d2 = 0; d2 < p.vw[col]; d2++)
+                    if (d2 != d)
+                        t = __fmul_rn(t, c2v[((size_t)p.v_cn[col * p.dv_max + d2] * p.dc_max + p.v_pos[col * p.dv_max + d2]) * q + x]);
+                v[x] = t;
+                s = __fadd_rn(s, t);
+            }
+            for (int x = 0; x < q; x++) v[x] = __fdiv_rn(v[x], s);
+        }
+        __syncthreads();
+        const int rounds = (M + groups - 1) / groups;
+        for (int r = 0; r < rounds; r++) {
+            const int row = r * groups + g;
+            const bool act = g < groups && row < M;
+            const int w = act ? p.cw[row] : 0;
+            for (int d = 0; d < w; d++) {
+                const float *v = v2c + ((size_t)p.c_vn[row * p.dc_max + d] * p.dv_max + p.c_pos[row * p.dc_max + d]) * q;
+                F[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])] = v[a];
+            }
+            __syncthreads();
+            wht_stage_all(F, q, w, a);
+            for (int d = 0; d < p.dc_max; d++) {  // same trip count for every group: barriers stay aligned
+                const bool on = d < w;
+                if (on) {
+                    float gy = 1.0f;
+                    bool first = true;
+                    for (int d2 = 0; d2 < w; d2++) {
+                        if (d2 == d) continue;
+                        gy = first ? F[d2 * q + a] : __fmul_rn(gy, F[d2 * q + a]);
+                        first = false;
+                    }
+                    G[a] = gy;
+                }
+                __syncthreads();
+                wht_stage_all(G, q, on ? 1 : 0, a);
+                if (on) {
+                    const float gv = G[gmul(p, a, p.c_gf[row * p.dc_max + d])];
+                    tmp[a] = gv > 1e-30f ? gv : 1e-30f;
+                }
+                __syncthreads();
+                if (on && a == 0) {
+                    float s = 0.0f;
+                    for (int x = 0; x < q; x++) s = __fadd_rn(s, tmp[x]);
+                    ssum[0] = s;
+                }
+                __syncthreads();
+                if (on) c2v[((size_t)row * p.dc_max + d) * q + a] = __fdiv_rn(tmp[a], ssum[0]);
+                __syncthreads();
+            }
+        }
+    }
+    if (tid == 0) {
+        if (p.iters_out) p.iters_out[f] = it;
+        if (p.ok_out) p.ok_out[f] = ok;
+    }
+}
+
 __global__ void __launch_bounds__(kNbThreads)
 nb_decode_kernel(const __grid_constant__ NbParams p)
 {
@@ -436,6 +567,8 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
         __syncthreads();
         if (p.algo == NB_ALGO_EMS)
             decode_ems(p, f, lch, LLR, c2v, v2c, topval, topsym, sym, smem, &s_fail);
+        else if (p.algo == NB_ALGO_FFT_BP)
+            decode_fftbp(p, f, lch, LLR, c2v, v2c, sym, smem, &s_fail);
         else
             decode_tmm(p, f, lch, LLR, c2v, sym, smem, &s_fail, p.algo == NB_ALGO_LAYERED_TMM);
         __syncthreads();
@@ -489,14 +622,16 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
 {
     if (!cc || !in || !hard_syms || !o || iters <= 0) return LDPC_ERR_ARG;
     if (o->struct_size != (int)sizeof(nb_decode_opts_t) || o->batch <= 0) return LDPC_ERR_ARG;
-    if (o->algo != NB_ALGO_EMS && o->algo != NB_ALGO_TMM && o->algo != NB_ALGO_LAYERED_TMM) return LDPC_ERR_ARG;
+    if (o->algo != NB_ALGO_EMS && o->algo != NB_ALGO_TMM && o->algo != NB_ALGO_LAYERED_TMM &&
+        o->algo != NB_ALGO_FFT_BP)
+        return LDPC_ERR_ARG;
     if (o->in_kind < 0 || o->in_kind > 2) return LDPC_ERR_ARG;
     nb_ldpc_code *c = const_cast<nb_ldpc_code *>(cc);
     if (o->algo == NB_ALGO_EMS && (o->ems_nm < 1 || o->ems_nm > kNmMax || o->ems_nc < 0)) return LDPC_ERR_UNSUPPORTED;
     if (o->in_kind == NB_IN_BPSK && c->n_const != 2) return LDPC_ERR_ARG;
     if (o->in_kind == NB_IN_QAM && c->n_const != c->q) return LDPC_ERR_ARG;
     if (o->in_kind != NB_IN_SYMBOL_LLR && !(o->sigma > 0.0f)) return LDPC_ERR_ARG;
-    if (o->algo != NB_ALGO_EMS)
+    if (o->algo == NB_ALGO_TMM || o->algo == NB_ALGO_LAYERED_TMM)
         for (int g : c->c_gf)
             if (g == 0) return LDPC_ERR_UNSUPPORTED;  // h^-1 does not exist (the reference exits with "Div 0 Error!")
     if (o->in_kind == NB_IN_BPSK && (c->cre[0] != 1.0f || c->cre[1] != -1.0f)) return LDPC_ERR_UNSUPPORTED;
@@ -516,6 +651,11 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
         ems_chunk = kNbThreads;
         while ((size_t)ems_chunk * q * sizeof(float) > 200 * 1024) ems_chunk /= 2;
         smem = (size_t)ems_chunk * q * sizeof(float);
+    } else if (o->algo == NB_ALGO_FFT_BP) {
+        if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;
+        for (int g : c->c_gf)
+            if (g == 0) return LDPC_ERR_UNSUPPORTED;  // multiplication by 0 is not a permutation
+        smem = (size_t)(kNbThreads / q) * ((size_t)(c->dc_max + 2) * q + 4) * sizeof(float);
     } else {
         const int groups = (o->algo == NB_ALGO_LAYERED_TMM) ? 1 : (kNbThreads / q > 0 ? kNbThreads / q : 1);
         if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA

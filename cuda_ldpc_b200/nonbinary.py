@@ -13,7 +13,7 @@ import numpy as np
 
 from ._lib import LdpcError, NbCodeInfo, NbDecodeOpts, lib
 
-ALGO_EMS, ALGO_TMM, ALGO_LAYERED_TMM = 0, 1, 3
+ALGO_EMS, ALGO_TMM, ALGO_LAYERED_TMM, ALGO_FFT_BP = 0, 1, 3, 4
 IN_SYMBOL_LLR, IN_BPSK, IN_QAM = 0, 1, 2
 
 

@@ -28,7 +28,7 @@ struct Args {
 
 static void usage()
 {
-    printf("usage: nb_ldpc_sim --matrix FILE --constellation FILE [--gf FILE] [--exp] [--algo ems|tmm|ltmm]\n"
+    printf("usage: nb_ldpc_sim --matrix FILE --constellation FILE [--gf FILE] [--exp] [--algo ems|tmm|ltmm|fftbp]\n"
            "       [--nm n --nc n] [--snr a b step] [--snrtype 0|1] [--maxit n] [--batch F] [--least-errors n]\n"
            "       [--least-frames n] [--max-frames n] [--gpus g] [--seed s] [--codeword FILE]\n");
 }
@@ -54,7 +54,7 @@ int main(int argc, char **argv)
         else if (s == "--constellation") a.constellation = next(), i++;
         else if (s == "--codeword") a.codeword = next(), i++;
         else if (s == "--exp") a.exp = 1;
-        else if (s == "--algo") { std::string m = next(); i++; a.algo = m == "tmm" ? NB_ALGO_TMM : m == "ltmm" ? NB_ALGO_LAYERED_TMM : NB_ALGO_EMS; }
+        else if (s == "--algo") { std::string m = next(); i++; a.algo = m == "tmm" ? NB_ALGO_TMM : m == "ltmm" ? NB_ALGO_LAYERED_TMM : m == "fftbp" ? NB_ALGO_FFT_BP : NB_ALGO_EMS; }
         else if (s == "--nm") a.nm = atoi(next()), i++;
         else if (s == "--nc") a.nc = atoi(next()), i++;
         else if (s == "--snr") a.snr_start = atof(next(1)), a.snr_stop = atof(next(2)), a.snr_step = atof(next(3)), i += 3;
@@ -104,7 +104,7 @@ int main(int argc, char **argv)
     const int kbits = (info.N - info.M) * info.p;
     printf("* %s  non-binary LDPC simulation\n* N=%d M=%d GF(%d) dv<=%d dc<=%d, %d-point constellation, decoder %s, max %d iterations\n",
            ldpc_version(), info.N, info.M, info.q, info.dv_max, info.dc_max, info.n_const,
-           a.algo == NB_ALGO_EMS ? "EMS" : a.algo == NB_ALGO_TMM ? "TMM" : "layered TMM", a.maxit);
+           a.algo == NB_ALGO_EMS ? "EMS" : a.algo == NB_ALGO_TMM ? "TMM" : a.algo == NB_ALGO_FFT_BP ? "FFT-BP" : "layered TMM", a.maxit);
     printf(" SNR   frames errFrames      FER         SER     avgIter  sec/frame   info Mbit/s\n");
     const int npts = (int)floor((a.snr_stop - a.snr_start) / a.snr_step + 1e-9) + 1;
     for (int pt = 0; pt < npts; pt++) {

@@ -180,6 +180,8 @@ int nb_ldpc_code_tables(const nb_ldpc_code_t *code, uint16_t *mul, uint16_t *inv
 #define NB_ALGO_EMS 0         /* NB/src/LDPC_Decoder.cpp:172-359  (scale 1/1.2)            */
 #define NB_ALGO_TMM 1         /* NB/src/LDPC_Decoder.cpp:361-542  (scale 0.8)              */
 #define NB_ALGO_LAYERED_TMM 3 /* NB/src/LDPC_Decoder.cpp:544-702                           */
+#define NB_ALGO_FFT_BP 4      /* NOT in the reference ("parity unpinned"): probability-domain BP,
+                                 check node = product in the Walsh-Hadamard domain; specified by the oracle */
 
 #define NB_IN_SYMBOL_LLR 0 /* fp32 [F][N][q-1]: L_ch as Demodulate produces it (log P(a)/P(0)) */
 #define NB_IN_BPSK 1       /* fp32 [F][N*p] real BPSK samples + sigma: fused Demodulate BPSK branch (NB/src/LDPC_Decoder.cpp:137-158) */

@@ -622,6 +622,123 @@ static int decode_tmm(nb_state *s, const float *L_ch, int maxit, int layered, in
     return ret;
 }
 
+/* ------------------------------------------------------------------ FFT-BP (parity unpinned)
+ * Probability-domain sum-product over GF(2^p); the reference has no such decoder, so these
+ * rules ARE the specification the CUDA kernel is held to (decisions / iteration counts; messages agree
+ * to float rounding because expf differs between libm and CUDA):
+ *   p_ch[0] = exp(0 - mx), p_ch[a] = exp(L_ch[a-1] - mx), mx = max(0, max L_ch); normalised by the sum
+ *   taken in ascending a.  c2v = 1 before the first iteration.
+ *   iteration: post[a] = (p_ch[a] * c2v_0[a]) * c2v_1[a] ...; decide = first argmax; syndrome stop with the
+ *   reference's counting (iterations-1 on success).
+ *   v2c_d[a] = p_ch[a] * prod_{d' != d, ascending} c2v_d'[a], normalised by its ascending sum.
+ *   check: P_d[h_d*x] = v2c_d[x]; F_d = WHT(P_d) (in-place butterflies, len = 1, 2, 4, ...: (u, v) ->
+ *   (u+v, u-v)); G = prod_{d' != d, ascending} F_d'; g = WHT(G); g = max(g, 1e-30f);
+ *   c2v_d[x] = g[h_d*x], normalised by its ascending sum. */
+static void wht(float *v, int q)
+{
+    for (int len = 1; len < q; len <<= 1)
+        for (int i = 0; i < q; i += 2 * len)
+            for (int j = i; j < i + len; j++) {
+                float a = v[j], b = v[j + len];
+                v[j] = a + b;
+                v[j + len] = a - b;
+            }
+}
+
+static void normalise(float *v, int q)
+{
+    float s = 0.0f;
+    for (int a = 0; a < q; a++) s = s + v[a];
+    for (int a = 0; a < q; a++) v[a] = v[a] / s;
+}
+
+static int decode_fftbp(nb_state *s, const float *L_ch, int maxit, int *out, int *iter_number)
+{
+    const nb_orc_code *c = s->c;
+    const int q = c->q, N = c->N, M = c->M;
+    float *pch = (float *)malloc((size_t)N * q * sizeof(float));
+    float *F = (float *)malloc((size_t)c->dc_max * q * sizeof(float)), *G = (float *)malloc((size_t)q * sizeof(float));
+    for (int col = 0; col < N; col++) {
+        float mx = 0.0f;
+        for (int a = 0; a < q - 1; a++)
+            if (L_ch[(size_t)col * (q - 1) + a] > mx) mx = L_ch[(size_t)col * (q - 1) + a];
+        float *p = pch + (size_t)col * q;
+        p[0] = expf(0.0f - mx);
+        for (int a = 1; a < q; a++) p[a] = expf(L_ch[(size_t)col * (q - 1) + a - 1] - mx);
+        normalise(p, q);
+    }
+    for (size_t i = 0; i < (size_t)M * c->dc_max * q; i++) s->c2v[i] = 1.0f;
+    int ret = 0;
+    *iter_number = 0;
+    while (*iter_number < maxit) {
+        (*iter_number)++;
+        for (int col = 0; col < N; col++) {
+            const float *p = pch + (size_t)col * q;
+            float best = -1.0f;
+            int bi = 0;
+            for (int a = 0; a < q; a++) {
+                float v = p[a];
+                for (int d = 0; d < c->vw[col]; d++)
+                    v = v * C2V(s, c->v_cn[col * c->dv_max + d], c->v_pos[col * c->dv_max + d])[a];
+                if (v > best) {
+                    best = v;
+                    bi = a;
+                }
+            }
+            out[col] = bi;
+        }
+        if (syndrome_first_fail(c, out)) {
+            (*iter_number)--;
+            ret = 1;
+            break;
+        }
+        for (int col = 0; col < N; col++)
+            for (int d = 0; d < c->vw[col]; d++) {
+                float *v = V2C(s, col, d);
+                for (int a = 0; a < q; a++) {
+                    float x = pch[(size_t)col * q + a];
+                    for (int d2 = 0; d2 < c->vw[col]; d2++)
+                        if (d2 != d) x = x * C2V(s, c->v_cn[col * c->dv_max + d2], c->v_pos[col * c->dv_max + d2])[a];
+                    v[a] = x;
+                }
+                normalise(v, q);
+            }
+        for (int row = 0; row < M; row++) {
+            const int w = c->cw[row];
+            for (int d = 0; d < w; d++) {
+                const float *v = V2C(s, c->c_vn[row * c->dc_max + d], c->c_pos[row * c->dc_max + d]);
+                const int h = c->c_gf[row * c->dc_max + d];
+                for (int x = 0; x < q; x++) F[d * q + c->mul[x * q + h]] = v[x];
+                wht(F + d * q, q);
+            }
+            for (int d = 0; d < w; d++) {
+                for (int y = 0; y < q; y++) {
+                    float g = 1.0f;
+                    int first = 1;
+                    for (int d2 = 0; d2 < w; d2++) {
+                        if (d2 == d) continue;
+                        g = first ? F[d2 * q + y] : g * F[d2 * q + y];
+                        first = 0;
+                    }
+                    G[y] = g;
+                }
+                wht(G, q);
+                float *m = C2V(s, row, d);
+                const int h = c->c_gf[row * c->dc_max + d];
+                for (int x = 0; x < q; x++) {
+                    float g = G[c->mul[x * q + h]];
+                    m[x] = g > 1e-30f ? g : 1e-30f;
+                }
+                normalise(m, q);
+            }
+        }
+    }
+    free(pch);
+    free(F);
+    free(G);
+    return ret;
+}
+
 int nb_orc_decode(const nb_orc_code *c, int algo, int sum_mode, const float *L_ch, int maxit, int ems_nm,
                   int ems_nc, int *out, int *iter_number)
 {
@@ -635,6 +752,8 @@ int nb_orc_decode(const nb_orc_code *c, int algo, int sum_mode, const float *L_c
     int r;
     if (algo == NB_ORC_EMS)
         r = decode_ems(&s, L_ch, maxit, ems_nm, ems_nc, out, iter_number);
+    else if (algo == NB_ORC_FFT_BP)
+        r = decode_fftbp(&s, L_ch, maxit, out, iter_number);
     else
         r = decode_tmm(&s, L_ch, maxit, algo == NB_ORC_LAYERED_TMM, out, iter_number);
     free(s.v2c); free(s.ent); free(s.c2v); free(s.LLR);

@@ -49,6 +49,8 @@ void nb_orc_demodulate(const nb_orc_code *c, float sigma, const float *rx, float
 #define NB_ORC_EMS 0
 #define NB_ORC_TMM 1
 #define NB_ORC_LAYERED_TMM 3
+#define NB_ORC_FFT_BP 4      /* NOT in the reference ("parity unpinned"): probability-domain BP with
+                                the check node as a Walsh-Hadamard-domain product; rules in nb_oracle.c */
 #define NB_ORC_SUM_LITERAL 0 /* the reference's running sum (inc before / dec after recursion) */
 #define NB_ORC_SUM_FRESH 1   /* sum of the inputs in ascending edge position, from 0.0f          */
 

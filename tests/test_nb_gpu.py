@@ -195,3 +195,35 @@ def test_nb_channel_statistic_and_cli(nb_oracle, gf_dir, meta):
     rows = [l.split() for l in r.stdout.splitlines() if l.startswith(" 2.0") or l.startswith(" 3.0")]
     assert len(rows) == 2 and float(rows[0][3]) > float(rows[1][3]) > 0
     assert abs(float(rows[1][3]) - fer_e) < 0.02  # same point (3 dB), same decoder
+
+
+@pytest.mark.parametrize("name,exp,snr,F", [("BDS", 0, 2.0, 48), ("C5", 1, 3.8, 32), ("C4", 1, 8.5, 32)])
+def test_fft_bp_vs_oracle(nb_oracle, gf_dir, meta, name, exp, snr, F):
+    """FFT-BP (Walsh-Hadamard check node) is NOT in the reference ("parity unpinned"): the kernel is held
+    to the oracle's specification — same decisions / iteration counts (expf differs in the last ulp
+    between libm and CUDA, so a marginal frame may differ), and it decodes at least as many frames as
+    the reference's TMM on the same noise."""
+    cfg = meta["configs"][name]
+    mt, gf, cs = paths(cfg, gf_dir)
+    h = orc_load(nb_oracle, cfg, gf_dir, exp)
+    code = m.NbLdpcCode(mt, gf, cs, coef_is_exponent=bool(exp))
+    N, q, p = code.N, code.q, code.p
+    L = N * p if cfg["n_qam"] == 2 else N
+    sym = np.zeros(N, np.int32)
+    tx = np.zeros(2 * L, np.float32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    sigma = nb_oracle.nb_orc_sigma(h, 0, snr)
+    seed = np.array([173, 173, 173], np.int32)
+    lch = np.zeros((F, N * (q - 1)), np.float32)
+    rx = np.zeros(2 * L, np.float32)
+    for f in range(F):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rx.ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rx.ctypes.data, lch[f].ctypes.data)
+    o_out = np.zeros((F, N), np.int32); o_it = np.zeros(F, np.int32); o_ok = np.zeros(F, np.int32)
+    nb_oracle.nb_orc_decode_batch(h, 4, 0, lch.ctypes.data, F, 20, 2, 2, o_out.ctypes.data, o_it.ctypes.data, o_ok.ctypes.data)
+    out, it, ok = code.decode(lch, 20, algo=m.ALGO_FFT_BP)
+    same = (out.astype(np.int32) == o_out).all(1) & (it == o_it) & (ok == o_ok)
+    assert same.sum() >= F - 1, (name, int(same.sum()))
+    assert same[o_ok == 1].all()
+    out_t, it_t, ok_t = code.decode(lch, 20, algo=m.ALGO_TMM)
+    assert ok.sum() >= ok_t.sum() and ok.sum() >= F // 2

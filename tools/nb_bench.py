@@ -11,6 +11,8 @@ CASES = [("C4 GF64 64QAM EMS(2,2)", "LDPC_N576_K288_GF64_d1_exp.txt", "GRAY_64QA
          ("C4 GF64 64QAM TMM", "LDPC_N576_K288_GF64_d1_exp.txt", "GRAY_64QAM.txt", 64, 10.0, m.ALGO_TMM, 8192),
          ("C4 GF64 64QAM layered TMM", "LDPC_N576_K288_GF64_d1_exp.txt", "GRAY_64QAM.txt", 64, 10.0, m.ALGO_LAYERED_TMM, 8192),
          ("BDS GF64 BPSK layered TMM", "BDS.576.288.GF.64.txt", "BPSK.txt", 2, 2.0, m.ALGO_LAYERED_TMM, 8192),
+         ("C4 GF64 64QAM FFT-BP", "LDPC_N576_K288_GF64_d1_exp.txt", "GRAY_64QAM.txt", 64, 10.0, m.ALGO_FFT_BP, 8192),
+         ("C5 GF256 BPSK FFT-BP", "LDPC_N576_K480_GF256_exp.txt", "BPSK.txt", 2, 4.5, m.ALGO_FFT_BP, 4096),
          ("C5 GF256 BPSK TMM", "LDPC_N576_K480_GF256_exp.txt", "BPSK.txt", 2, 4.5, m.ALGO_TMM, 4096),
          ("C5 GF256 BPSK layered TMM", "LDPC_N576_K480_GF256_exp.txt", "BPSK.txt", 2, 4.5, m.ALGO_LAYERED_TMM, 4096)]
 print(torch.cuda.get_device_name(0))
