@@ -14,7 +14,7 @@ import numpy as np
 from ._lib import CodeInfo, DecodeOpts, LdpcError, lib
 
 LAYOUT_NF, LAYOUT_FN = 0, 1
-DTYPE_FP32, DTYPE_FP16, DTYPE_INT8 = 0, 1, 2
+DTYPE_FP32, DTYPE_FP16, DTYPE_INT8, DTYPE_CHANNEL = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 SCHED_FLOODING, SCHED_LAYERED = 0, 1
 EXIT_NONE, EXIT_GENIE, EXIT_SYNDROME = 0, 1, 2
@@ -87,6 +87,40 @@ class LdpcCode:
                 raise TypeError(f"unknown decode option {k}")
             setattr(o, k, v)
         return o
+
+    def decode_channel(self, F, iters, sigma, *, seed=173, first_frame=0, codeword=None, early_exit=EXIT_SYNDROME,
+                       out_format=OUT_BITPACK, llr_scale=8.0, msg_max=31, beta_num=0, beta_shift=0, stream=None, out=None,
+                       iters_out=None, ok_out=None, device=None):
+        """Layered int8 decode of F frames whose channel values are generated INSIDE the kernel
+        (y = 1 - 2c + sigma*n, the Philox stream of ldpc_awgn_bpsk keyed by the global frame index):
+        the fused form of AWGNChannel_CPU + cudaMemcpy + LDPC_Decoder_GPU (Simulation.cu:137-143).
+        codeword: CUDA uint8 tensor [N] or None (all-zero).  Device path only."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        if out is None:
+            out = torch.empty(self.out_bytes(F, out_format), dtype=torch.uint8, device=dev)
+        if iters_out is None:
+            iters_out = torch.empty(F, dtype=torch.int32, device=dev)
+        if ok_out is None:
+            ok_out = torch.empty(F, dtype=torch.int32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        o = self.make_opts(F, layout=LAYOUT_NF, llr_dtype=DTYPE_CHANNEL, mem_space=MEM_DEVICE, schedule=SCHED_LAYERED,
+                           msg_dtype=DTYPE_INT8, early_exit=early_exit, out_format=out_format, llr_scale=llr_scale,
+                           msg_max=msg_max, beta_num=beta_num, beta_shift=beta_shift, iters_out=iters_out.data_ptr(),
+                           ok_out=ok_out.data_ptr(), stream=stream, channel_sigma=float(sigma), channel_seed=int(seed),
+                           channel_first_frame=int(first_frame),
+                           channel_codeword=codeword.data_ptr() if codeword is not None else None)
+        rc = lib.ldpc_decode_batch(self._h, None, out.data_ptr(), int(iters), C.byref(o))
+        if rc < 0:
+            raise LdpcError(rc, "ldpc_decode_batch")
+        if out_format == OUT_INT32_REF:
+            D = out.view(torch.int32).view(self.N + 1, F)
+        elif out_format == OUT_U8:
+            D = out.view(self.N, F)
+        else:
+            D = out.view(torch.int32).view(F, (self.N + 31) // 32)
+        return DecodeResult(D, iters_out, ok_out, rc)
 
     def decode(self, llr, iters, *, schedule=SCHED_FLOODING, msg_dtype=None, layout=LAYOUT_NF, early_exit=EXIT_NONE,
                out_format=OUT_INT32_REF, alpha=1.0, llr_scale=8.0, msg_max=127, beta_num=0, beta_shift=0,

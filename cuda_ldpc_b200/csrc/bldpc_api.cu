@@ -143,6 +143,9 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
         a.dbg_rec = nullptr;
         a.scratch = sl + in_b + out_b + 2 * fl_b;
         a.scratch_bytes = align_up(rec_bytes);
+        a.ch_sigma = 0.0f;
+        a.ch_seed = a.ch_first = 0;
+        a.ch_cw = nullptr;
         rc = launch_layered_i8(c, a, st, &launches);
         if (rc != LDPC_OK) return rc;
         unsigned char *h_out = reinterpret_cast<unsigned char *>(hard_bits);
@@ -203,12 +206,14 @@ extern "C" size_t ldpc_out_bytes(const ldpc_code_t *c, int F, int fmt)
 extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *hard_bits, int iters,
                                  const ldpc_decode_opts_t *o)
 {
-    if (!c || !llr || !hard_bits || !o || iters <= 0) return LDPC_ERR_ARG;
+    if (!c || !hard_bits || !o || iters <= 0) return LDPC_ERR_ARG;
+    const bool fused_channel = (o->llr_dtype == LDPC_DTYPE_CHANNEL);
+    if (!llr && !fused_channel) return LDPC_ERR_ARG;
     if (o->struct_size != (int)sizeof(ldpc_decode_opts_t)) return LDPC_ERR_ARG;
     const int F = o->batch;
     if (F <= 0) return LDPC_ERR_ARG;
     if (o->layout != LDPC_LAYOUT_NF && o->layout != LDPC_LAYOUT_FN) return LDPC_ERR_ARG;
-    if (o->llr_dtype < 0 || o->llr_dtype > 2 || o->out_format < 0 || o->out_format > 2) return LDPC_ERR_ARG;
+    if (o->llr_dtype < 0 || o->llr_dtype > 3 || o->out_format < 0 || o->out_format > 2) return LDPC_ERR_ARG;
     if (o->early_exit < 0 || o->early_exit > 2) return LDPC_ERR_ARG;
     if (o->schedule != LDPC_SCHED_FLOODING && o->schedule != LDPC_SCHED_LAYERED) return LDPC_ERR_ARG;
     // "flooding" below = the streaming fp32 paths (messages in HBM, hard bits emitted by a conversion
@@ -218,6 +223,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     if (flooding && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
     if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8) return LDPC_ERR_UNSUPPORTED;
     if (o->schedule == LDPC_SCHED_LAYERED && o->early_exit == LDPC_EXIT_GENIE) return LDPC_ERR_UNSUPPORTED;
+    if (fused_channel && (flooding || !(o->channel_sigma >= 0.0f))) return LDPC_ERR_UNSUPPORTED;  // layered int8 only
     int rc = ensure_device(c);
     if (rc != LDPC_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
@@ -225,11 +231,11 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     // large host batches: chunked copy/compute overlap (2 groups per SM and chunk).  Measured on B200 for
     // the bench workload (1.45 GB of fp32 per call, pinned): 37.9 ms unchunked -> 28.5 ms with 8 chunks,
     // i.e. PCIe-bound (55 GB/s) instead of copy + decode in series (profiles/r01_h2d_probe.txt).
-    if (host && !flooding && o->msg_dtype == LDPC_DTYPE_INT8 && !o->debug_app && !o->debug_msgs) {
+    if (host && !flooding && !fused_channel && o->msg_dtype == LDPC_DTYPE_INT8 && !o->debug_app && !o->debug_msgs) {
         const int Fc = 4 * c->num_sms * 2;
         if (F >= 2 * Fc) return decode_host_pipelined(c, llr, hard_bits, iters, o, Fc);
     }
-    const size_t in_bytes = (size_t)c->N * F * dtype_bytes(o->llr_dtype);
+    const size_t in_bytes = fused_channel ? 0 : (size_t)c->N * F * dtype_bytes(o->llr_dtype);
     const size_t out_bytes = ldpc_out_bytes(c, F, o->out_format);
     const size_t dbg_app_bytes =
         o->debug_app ? (size_t)c->N * F * (layered_f32 ? 4 : (flooding ? 0 : 1)) : 0;
@@ -270,7 +276,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     if (host) {
         d_in = base + o_in;
         d_out = base + o_out;
-        LDPC_CUDA_TRY(cudaMemcpyAsync(base + o_in, llr, in_bytes, cudaMemcpyHostToDevice, st));
+        if (in_bytes) LDPC_CUDA_TRY(cudaMemcpyAsync(base + o_in, llr, in_bytes, cudaMemcpyHostToDevice, st));
         d_it = reinterpret_cast<int *>(base + o_it);
         d_ok = reinterpret_cast<int *>(base + o_ok);
         if (o->debug_app) d_dapp = base + o_dapp;
@@ -331,6 +337,10 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         a.dbg_rec = d_dmsg;
         a.scratch = base + o_layer;
         a.scratch_bytes = layered_extra;
+        a.ch_sigma = o->channel_sigma;
+        a.ch_seed = o->channel_seed;
+        a.ch_first = o->channel_first_frame;
+        a.ch_cw = o->channel_codeword;
         rc = launch_layered_i8(c, a, st, &launches);
         if (rc != LDPC_OK) return rc;
         if (host && o->debug_msgs)

@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include "common.h"
+#include "philox.cuh"
 
 namespace ldpcb {
 
@@ -36,6 +37,10 @@ struct LayeredParams {
     float msg_max;
     float beta_mul;         // beta_num / 2^beta_shift
     float beta_bias;        // 0.5 - 2^-(beta_shift+1)
+    float ch_sigma;         // fused channel: sigma, Philox key, first global frame, codeword bits
+    unsigned ch_k0, ch_k1;
+    unsigned long long ch_first;
+    const unsigned char *ch_cw;
     int scale_on;           // beta_num != 0
     unsigned c64;           // 0x64646464: kept in a register so PRMT can take the selector as its immediate
     // kernel-ready layer tables: entry e = {column-block byte offset c*Z*4, shift byte offset s*4}
@@ -429,9 +434,31 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         unsigned valid = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) valid |= (f0 + j < F) ? (1u << j) : 0u;
+        // ---- fused channel: generate y = 1 - 2c + sigma*n for the 4 frames of the group right here (one
+        // Philox call = 4 consecutive bits of one frame), quantise, store — no channel buffer in HBM at all
+        if (p.llr_dtype == LDPC_DTYPE_CHANNEL) {
+            for (int nb = tid; nb < (N + 3) / 4; nb += T) {
+                float g[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) awgn_normals4(p.ch_first + (unsigned long long)(f0 + j), nb, p.ch_k0, p.ch_k1, g[j]);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int n = 4 * nb + b;
+                    if (n >= N) break;
+                    const int bit = p.ch_cw ? (p.ch_cw[n] & 1) : 0;
+                    unsigned w = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int q = ((valid >> j) & 1u) ? quant(awgn_bpsk_sample(bit, p.ch_sigma, g[j][b]), p.scale) : 127;
+                        w |= (unsigned)(q + 128) << (8 * j);
+                    }
+                    appw[n] = w;
+                }
+            }
+        }
         // ---- load + quantise: q = sat127(rint(y * scale)), stored biased by 128
 #pragma unroll 4
-        for (int n = tid; n < N; n += T) {
+        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL) ? N : tid; n < N; n += T) {
             int q[4];
             if (p.llr_dtype == LDPC_DTYPE_FP32) {
                 const float *y = reinterpret_cast<const float *>(p.llr);
@@ -614,6 +641,11 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.msg_max = (float)a.msg_max;
     p.beta_mul = (float)a.beta_num / (float)(1 << a.beta_shift);
     p.beta_bias = 0.5f - 1.0f / (float)(2 << a.beta_shift);
+    p.ch_sigma = a.ch_sigma;
+    p.ch_k0 = (unsigned)a.ch_seed;
+    p.ch_k1 = (unsigned)(a.ch_seed >> 32);
+    p.ch_first = a.ch_first;
+    p.ch_cw = a.ch_cw;
     p.scale_on = a.beta_num != 0;
     p.c64 = 0x64646464u;
     p.lt = c->lt;

@@ -7,32 +7,9 @@
 //  * ldpc_statistic replaces Statistic (B/Simulation.cu:245-285) with the same counter semantics,
 //    reduced on the device.
 #include "common.h"
+#include "philox.cuh"
 
 namespace ldpcb {
-
-__host__ __device__ __forceinline__ void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1)
-{
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-    c[0] = n0;
-    c[1] = lo1;
-    c[2] = n2;
-    c[3] = lo0;
-}
-
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        philox_round(c, k0, k1);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-
-// uniform in (0, 1]: never 0, so log() is finite
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
 
 // one thread = 4 consecutive bits n..n+3 of one frame (one Philox call, two Box-Muller pairs)
 __global__ void __launch_bounds__(256)
@@ -52,24 +29,14 @@ awgn_bpsk_kernel(float *__restrict__ y, int N, int F, int layout, float sigma, u
         f = (int)(tid / NB);
     }
     const unsigned long long gf = first_frame + (unsigned long long)f;
-    uint32_t c[4] = {(uint32_t)gf, (uint32_t)(gf >> 32), (uint32_t)nb, 0x4C445043u /* "LDPC" */};
-    philox4x32_10(c, k0, k1);
     float g[4];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const float r = sqrtf(-2.0f * __logf(u01(c[2 * h])));
-        float sn, cs;
-        __sincosf(6.283185307179586f * u01(c[2 * h + 1]), &sn, &cs);
-        g[2 * h] = r * cs;
-        g[2 * h + 1] = r * sn;
-    }
+    awgn_normals4(gf, nb, k0, k1, g);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int n = nb * 4 + j;
         if (n >= N) break;
-        const float x = 1.0f - 2.0f * (cw ? (float)cw[n] : 0.0f);  // BPSK, B/LDPC_Encoder.cu:10-17
         const size_t o = (layout == LDPC_LAYOUT_NF) ? (size_t)n * F + f : (size_t)f * N + n;
-        y[o] = x + sigma * g[j];
+        y[o] = awgn_bpsk_sample(cw ? (cw[n] & 1) : 0, sigma, g[j]);  // BPSK, B/LDPC_Encoder.cu:10-17
     }
 }
 

@@ -89,6 +89,10 @@ struct LayeredArgs {
     void *dbg_app, *dbg_rec;
     void *scratch;         // device scratch for the check records
     size_t scratch_bytes;
+    // fused channel (llr_dtype == LDPC_DTYPE_CHANNEL)
+    float ch_sigma;
+    unsigned long long ch_seed, ch_first;
+    const unsigned char *ch_cw;
 };
 // bytes of record scratch the layered kernels want for a batch of F frames
 int layered_i8_scratch_bytes(const ldpc_code *code, int F, int beta_num, size_t *bytes);

@@ -64,7 +64,9 @@ class CudaBatchRunner:
         import torch
         self.torch, self.code, self.batch, self.maxit, self.seed = torch, code, batch, maxit, seed
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.y = torch.empty(code.N * batch, dtype=torch.float32, device=dev)
+        # flooding fp32 reads a channel buffer; the layered int8 decoder generates the channel itself
+        self.fused = schedule == B.SCHED_LAYERED
+        self.y = None if self.fused else torch.empty(code.N * batch, dtype=torch.float32, device=dev)
         self.out = torch.empty(code.out_bytes(batch, B.OUT_BITPACK), dtype=torch.uint8, device=dev)
         self.iters = torch.empty(batch, dtype=torch.int32, device=dev)
         self.ok = torch.empty(batch, dtype=torch.int32, device=dev)
@@ -79,12 +81,17 @@ class CudaBatchRunner:
     def run(self, sigma, first_frame):
         st = self.torch.cuda.current_stream().cuda_stream
         cw = self.cw.data_ptr() if self.cw is not None else None
-        rc = lib.ldpc_awgn_bpsk(self.code.handle, self.y.data_ptr(), self.batch, B.LAYOUT_NF, float(sigma),
-                                int(self.seed), int(first_frame), cw, st)
-        if rc < 0:
-            raise LdpcError(rc, "ldpc_awgn_bpsk")
-        self.code.decode(self.y.view(self.code.N, self.batch), self.maxit, out=self.out, iters_out=self.iters,
-                         ok_out=self.ok, **self.kw)
+        if self.fused:
+            kw = {k: v for k, v in self.kw.items() if k != "schedule"}
+            self.code.decode_channel(self.batch, self.maxit, sigma, seed=self.seed, first_frame=first_frame,
+                                     codeword=self.cw, out=self.out, iters_out=self.iters, ok_out=self.ok, **kw)
+        else:
+            rc = lib.ldpc_awgn_bpsk(self.code.handle, self.y.data_ptr(), self.batch, B.LAYOUT_NF, float(sigma),
+                                    int(self.seed), int(first_frame), cw, st)
+            if rc < 0:
+                raise LdpcError(rc, "ldpc_awgn_bpsk")
+            self.code.decode(self.y.view(self.code.N, self.batch), self.maxit, out=self.out, iters_out=self.iters,
+                             ok_out=self.ok, **self.kw)
         rc = lib.ldpc_statistic(self.code.handle, self.out.data_ptr(), B.OUT_BITPACK, self.ok.data_ptr(),
                                 self.iters.data_ptr(), self.batch, self.code.K, cw, self.cnt.data_ptr(), st)
         if rc < 0:

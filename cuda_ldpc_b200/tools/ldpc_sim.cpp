@@ -144,12 +144,22 @@ int main(int argc, char **argv)
                     ldpc_decode_opts_t o;
                     ldpc_decode_opts_default(&o);
                     o.batch = a.batch; o.mem_space = LDPC_MEM_DEVICE; o.schedule = a.schedule; o.msg_dtype = a.msg;
-                    o.early_exit = a.exit_mode; o.out_format = LDPC_OUT_INT32_REF; o.llr_scale = a.llr_scale;
+                    o.early_exit = a.exit_mode; o.llr_scale = a.llr_scale;
                     o.msg_max = a.msg_max; o.beta_num = a.beta_num; o.beta_shift = a.beta_shift;
                     o.iters_out = x.iters; o.ok_out = x.ok; o.stream = x.st;
-                    int rc = ldpc_awgn_bpsk(x.code, x.y, a.batch, LDPC_LAYOUT_NF, sigma, a.seed, first, x.cw, x.st);
-                    if (rc >= 0) rc = ldpc_decode_batch(x.code, x.y, x.out, a.maxit, &o);
-                    if (rc >= 0) rc = ldpc_statistic(x.code, x.out, LDPC_OUT_INT32_REF, nullptr, x.iters, a.batch, info.K, x.cw, x.cnt, x.st);
+                    int rc;
+                    if (a.schedule == LDPC_SCHED_LAYERED) {
+                        // channel fused into the decoder's load phase, bit-packed decisions: no F*N buffer anywhere
+                        o.llr_dtype = LDPC_DTYPE_CHANNEL; o.out_format = LDPC_OUT_BITPACK;
+                        o.channel_sigma = sigma; o.channel_seed = a.seed; o.channel_first_frame = first; o.channel_codeword = x.cw;
+                        rc = ldpc_decode_batch(x.code, nullptr, x.out, a.maxit, &o);
+                        if (rc >= 0) rc = ldpc_statistic(x.code, x.out, LDPC_OUT_BITPACK, x.ok, x.iters, a.batch, info.K, x.cw, x.cnt, x.st);
+                    } else {
+                        o.out_format = LDPC_OUT_INT32_REF;
+                        rc = ldpc_awgn_bpsk(x.code, x.y, a.batch, LDPC_LAYOUT_NF, sigma, a.seed, first, x.cw, x.st);
+                        if (rc >= 0) rc = ldpc_decode_batch(x.code, x.y, x.out, a.maxit, &o);
+                        if (rc >= 0) rc = ldpc_statistic(x.code, x.out, LDPC_OUT_INT32_REF, nullptr, x.iters, a.batch, info.K, x.cw, x.cnt, x.st);
+                    }
                     x.rc = rc;
                 });
             }

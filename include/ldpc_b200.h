@@ -68,6 +68,9 @@ int ldpc_code_tables(const ldpc_code_t *code, int *H, int *Wc, int *Wv, int *add
 #define LDPC_DTYPE_FP32 0
 #define LDPC_DTYPE_FP16 1
 #define LDPC_DTYPE_INT8 2
+#define LDPC_DTYPE_CHANNEL 3 /* no input buffer: the channel values are generated inside the layered int8 kernel
+                                (same Philox stream as ldpc_awgn_bpsk, fused into the load of the first iteration);
+                                `llr` is ignored, see ldpc_decode_opts_t.channel_*                              */
 
 #define LDPC_MEM_HOST 0
 #define LDPC_MEM_DEVICE 1
@@ -103,6 +106,12 @@ typedef struct {
     void *stream;      /* cudaStream_t, NULL = default stream                                       */
     void *debug_app;   /* optional device/host buffer receiving the final APP (layered) — tests     */
     void *debug_msgs;  /* optional buffer receiving final messages / check records — tests          */
+    /* fused channel (llr_dtype == LDPC_DTYPE_CHANNEL): y = 1 - 2c + sigma*N(0,1), Philox keyed by
+     * (channel_seed, channel_first_frame + f, bit/4) exactly like ldpc_awgn_bpsk                    */
+    float channel_sigma;
+    uint64_t channel_seed;
+    uint64_t channel_first_frame;
+    const uint8_t *channel_codeword; /* device uint8 [N] broadcast to all frames, NULL = all-zero      */
 } ldpc_decode_opts_t;
 
 void ldpc_decode_opts_default(ldpc_decode_opts_t *opts);

@@ -82,6 +82,28 @@ def test_awgn_statistics_and_shard_independence():
 
 
 @pytest.mark.gpu
+def test_fused_channel_equals_awgn_then_decode():
+    """LDPC_DTYPE_CHANNEL (channel generated inside the layered kernel's load phase) gives bit for bit the
+    result of ldpc_awgn_bpsk followed by ldpc_decode_batch, for any sharding offset and a non-zero codeword."""
+    import torch
+    code = m.LdpcCode(os.path.join(BL, "PON_LDPC.txt"), 12, 69, 256)
+    u = np.random.default_rng(3).integers(0, 2, code.K).astype(np.uint8)
+    cw = np.zeros(code.N, np.uint8)
+    assert m.lib.ldpc_encode(code.handle, u.ctypes.data, cw.ctypes.data) == 0
+    cwd = torch.as_tensor(cw, device="cuda")
+    F, sigma, first = 203, 0.42, 12345
+    y = torch.empty(code.N * F, dtype=torch.float32, device="cuda")
+    assert m.lib.ldpc_awgn_bpsk(code.handle, y.data_ptr(), F, m.LAYOUT_NF, sigma, 99, first, cwd.data_ptr(),
+                                torch.cuda.current_stream().cuda_stream) >= 0
+    kw = dict(early_exit=m.EXIT_SYNDROME, out_format=m.OUT_BITPACK, msg_max=31, beta_num=1, beta_shift=3)
+    a = code.decode(y.view(code.N, F), 12, schedule=m.SCHED_LAYERED, **kw)
+    b = code.decode_channel(F, 12, sigma, seed=99, first_frame=first, codeword=cwd, **kw)
+    torch.cuda.synchronize()
+    assert (a.D == b.D).all() and (a.iters == b.iters).all() and (a.ok == b.ok).all()
+    assert b.ok.float().mean() > 0.3 and a.launches == 1 and b.launches == 1
+
+
+@pytest.mark.gpu
 def test_statistic_kernel_all_formats():
     import torch
     code = m.LdpcCode(os.path.join(BL, "J4_L24_Z96_BlockH.txt"))
