@@ -30,6 +30,7 @@ struct LayeredParams {
     signed char *dbg_app;
     unsigned *dbg_rec;
     uint4 *rec;             // scratch: per CTA, M records of REC_U4 uint4
+    int *work_counter;      // dynamic group scheduling (early exit), or nullptr
     int llr_dtype, layout, out_format;
     int F, N, Z, J, M;
     int iters, exit_mode, num_groups;
@@ -429,7 +430,19 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     const __half2 bmul = __float2half2_rn(p.beta_mul);
     const __half2 nbias = __float2half2_rn(-p.beta_bias);
 
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    // Group scheduling: with early exit the decode time of a group depends on its slowest frame, so groups
+    // are handed out through an atomic counter (first come, first served); with fixed iterations every
+    // group costs the same and a static stride keeps the next group known (L2 prefetch below).
+    __shared__ int s_next;
+    const bool dynamic = p.work_counter != nullptr;
+    int g = blockIdx.x;
+    for (;; g += gridDim.x) {
+        if (dynamic) {
+            if (tid == 0) s_next = atomicAdd(p.work_counter, 1);
+            __syncthreads();
+            g = s_next;
+        }
+        if (g >= p.num_groups) break;
         const int f0 = 4 * g;
         unsigned valid = 0;
 #pragma unroll
@@ -496,7 +509,8 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         if (tid == 0) s_fail = 0u;
         __syncthreads();
         // pull the channel values of this CTA's next group towards L2 while this group is decoded
-        if (g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 && p.layout == LDPC_LAYOUT_NF) {
+        if (!dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
+            p.layout == LDPC_LAYOUT_NF) {
             const float *y = reinterpret_cast<const float *>(p.llr) + 4 * (size_t)(g + gridDim.x);
             for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
         }
@@ -604,7 +618,7 @@ int layered_i8_scratch_bytes(const ldpc_code *c, int F, int, size_t *bytes)
     I8Plan pl;
     int rc = plan_i8(c, F, &pl);
     if (rc != LDPC_OK) return rc;
-    *bytes = (size_t)pl.grid * c->M * pl.u4 * sizeof(uint4);
+    *bytes = (size_t)pl.grid * c->M * pl.u4 * sizeof(uint4) + 256;  // + the work counter
     return LDPC_OK;
 }
 
@@ -616,7 +630,8 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     I8Plan pl;
     int rc = plan_i8(c, a.F, &pl);
     if (rc != LDPC_OK) return rc;
-    if ((size_t)pl.grid * c->M * pl.u4 * sizeof(uint4) > a.scratch_bytes) return LDPC_ERR_NOMEM;
+    const size_t rec_bytes = (size_t)pl.grid * c->M * pl.u4 * sizeof(uint4);
+    if (rec_bytes + 256 > a.scratch_bytes) return LDPC_ERR_NOMEM;
     LayeredParams p;
     memset(&p, 0, sizeof(p));
     p.llr = a.llr;
@@ -626,6 +641,10 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.dbg_app = reinterpret_cast<signed char *>(a.dbg_app);
     p.dbg_rec = reinterpret_cast<unsigned *>(a.dbg_rec);
     p.rec = reinterpret_cast<uint4 *>(a.scratch);
+    if (a.exit_mode == LDPC_EXIT_SYNDROME) {
+        p.work_counter = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(a.scratch) + rec_bytes);
+        LDPC_CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
+    }
     p.llr_dtype = a.llr_dtype;
     p.layout = a.layout;
     p.out_format = a.out_format;
