@@ -80,71 +80,103 @@ __device__ void syndrome(const NbParams &p, const uint16_t *sym, int *fail)
 }
 
 // ---- EMS, NB/src/LDPC_Decoder.cpp:172-359 -------------------------------------------------------
-// One (check, output edge) task: E[s] = max over conf(q,1) U conf(Nm,Nc) of the fresh sum.
-// E lives in shared memory, transposed (E[a*stride + slot]) so that threads hit distinct banks.
-__device__ void ems_check_task(const NbParams &p, int row, int dc, const float *v2c, const uint16_t *topsym,
-                               const float *topval, float *c2v, float *E, int stride)
+// One (check, output edge) task per WARP: E[s] = max over conf(q,1) U conf(Nm,Nc) of the fresh sum
+// (inputs summed from 0.0f in ascending edge position, the oracle's `fresh` rule).  Lane l owns the
+// syndromes s = l, l+32, ...: for a fixed deviating input j the map a -> s is a bijection (h_j != 0), so
+// every lane finds "its" symbol a = h_j^-1 (s ^ s_rest) directly and no two lanes ever write the same
+// E[s] — no atomics, no serial enumeration of the q*(dc-1) single-deviation leaves by one thread.
+// E of the warp goes to shared memory only for the final permuted read-out.
+struct EmsWarpShared {   // per warp, in shared memory
+    float *E;             // [q]
+    int *ie, *ih;         // [32] inputs of the task: edge slot in v2c/top, coefficient
+    float *tval;          // [32][kNmMax] best values of every input
+    int *tsym;            // [32][kNmMax] and their symbols
+};
+__host__ __device__ constexpr size_t ems_warp_floats(int q) { return (size_t)q + 32 + 32 + 32 * kNmMax * 2; }
+
+__device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const float *v2c, const uint16_t *topsym,
+                                    const float *topval, float *c2v, const EmsWarpShared &ws, int lane)
 {
-    const int q = p.q, w = p.cw[row];
-    for (int a = 0; a < q; a++) E[a * stride] = -INFINITY;
-    // inputs in ascending edge position, the output edge left out
-    int n = 0;
-    int ie[32], ih[32];
-    for (int b = 0; b < w; b++) {
-        if (b == dc) continue;
-        ie[n] = p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b];  // edge slot in v2c/top
-        ih[n] = p.c_gf[row * p.dc_max + b];
-        n++;
-    }
-    // conf(q,1): every input at its best symbol, at most one input at any other symbol
-    int s0 = 0;
-    for (int j = 0; j < n; j++) s0 ^= gmul(p, topsym[ie[j] * kNmMax], ih[j]);
-    {
-        float sum = 0.0f;
-        for (int j = 0; j < n; j++) sum = __fadd_rn(sum, topval[ie[j] * kNmMax]);
-        if (sum > E[s0 * stride]) E[s0 * stride] = sum;
-    }
-    for (int j = 0; j < n; j++) {
-        const int best = topsym[ie[j] * kNmMax];
-        const int sj = s0 ^ gmul(p, best, ih[j]);
-        const float *vj = v2c + (size_t)ie[j] * q;
-        for (int a = 0; a < q; a++) {
-            if (a == best) continue;
-            float sum = 0.0f;
-            for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? vj[a] : topval[ie[i] * kNmMax]);
-            const int s = sj ^ gmul(p, a, ih[j]);
-            if (sum > E[s * stride]) E[s * stride] = sum;
+    const int q = p.q, w = p.cw[row], n = w - 1;
+    if (lane < n) {  // inputs in ascending edge position, the output edge left out
+        const int b = lane + (lane >= dc);
+        const int e = p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b];
+        ws.ie[lane] = e;
+        ws.ih[lane] = p.c_gf[row * p.dc_max + b];
+        for (int k = 0; k < p.nm; k++) {
+            ws.tval[lane * kNmMax + k] = topval[e * kNmMax + k];
+            ws.tsym[lane * kNmMax + k] = topsym[e * kNmMax + k];
         }
     }
-    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1 (odometer with pruning)
+    __syncwarp();
+    int s0 = 0;
+    float sum_top = 0.0f;
+    for (int j = 0; j < n; j++) {
+        s0 ^= gmul(p, ws.tsym[j * kNmMax], ws.ih[j]);
+        sum_top = __fadd_rn(sum_top, ws.tval[j * kNmMax]);
+    }
     const int Nc = (p.nc == p.dc_max - 1) ? w - 1 : p.nc;  // :297-304
-    int ks[32];
-    for (int j = 0; j < n; j++) ks[j] = 0;
+    for (int s = lane; s < q; s += 32) {
+        float e = (s == s0) ? sum_top : -INFINITY;
+        // conf(q,1): input j at the symbol a that makes the syndrome s, everybody else at their best
+        for (int j = 0; j < n; j++) {
+            const int best = ws.tsym[j * kNmMax], hj = ws.ih[j];
+            const float *vj = v2c + (size_t)ws.ie[j] * q;
+            if (hj != 0) {
+                const int a = gmul(p, __ldg(p.inv + hj), s ^ s0 ^ gmul(p, best, hj));
+                if (a != best) {
+                    const float va = vj[a];
+                    float sum = 0.0f;
+                    for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? va : ws.tval[i * kNmMax]);
+                    e = fmaxf(e, sum);
+                }
+            } else if (s == s0) {  // coefficient 0 (raw *_exp files): every symbol of input j lands on s0
+                for (int a = 0; a < q; a++) {
+                    if (a == best) continue;
+                    float sum = 0.0f;
+                    for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? vj[a] : ws.tval[i * kNmMax]);
+                    e = fmaxf(e, sum);
+                }
+            }
+        }
+        ws.E[s] = e;
+    }
+    __syncwarp();
+    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1 — few leaves; every lane walks the same
+    // odometer (digits packed 2 bits per input in a register) and keeps the leaves on its own syndromes
+    unsigned long long ks = 0;
+    int diff = 0;
     while (true) {
         int s = 0;
         float sum = 0.0f;
         for (int j = 0; j < n; j++) {
-            s ^= gmul(p, topsym[ie[j] * kNmMax + ks[j]], ih[j]);
-            sum = __fadd_rn(sum, topval[ie[j] * kNmMax + ks[j]]);
+            const int k = (int)((ks >> (2 * j)) & 3ull);
+            s ^= gmul(p, ws.tsym[j * kNmMax + k], ws.ih[j]);
+            sum = __fadd_rn(sum, ws.tval[j * kNmMax + k]);
         }
-        if (sum > E[s * stride]) E[s * stride] = sum;
+        if ((s & 31) == lane && sum > ws.E[s]) ws.E[s] = sum;
         int j = n - 1;
-        for (; j >= 0; j--) {
-            ks[j]++;
-            int diff = 0;
-            for (int i = 0; i <= j; i++) diff += ks[i] != 0;
-            if (ks[j] < p.nm && diff <= Nc) break;
-            ks[j] = 0;
+        for (; j >= 0; j--) {  // increment digit j; reset and carry when it overflows or breaks the budget
+            const int k = (int)((ks >> (2 * j)) & 3ull);
+            if (k == 0) diff++;
+            if (k + 1 < p.nm && diff <= Nc) {
+                ks += 1ull << (2 * j);
+                break;
+            }
+            ks &= ~(3ull << (2 * j));
+            diff--;
         }
         if (j < 0) break;
     }
+    __syncwarp();
     const int h = p.c_gf[row * p.dc_max + dc];
     float *m = c2v + ((size_t)row * p.dc_max + dc) * q;
-    const float e0 = E[0];
-    for (int k = 1; k < q; k++) {
-        const float d = __fsub_rn(E[gmul(p, k, h) * stride], e0);
+    const float e0 = ws.E[0];
+    for (int k = 1 + lane; k < q; k += 32) {
+        const float d = __fsub_rn(ws.E[gmul(p, k, h)], e0);
         m[k - 1] = (float)((double)d / 1.2);  // float difference, double division (:309)
     }
+    __syncwarp();
 }
 
 __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, float *c2v, float *v2c, float *topval,
@@ -220,16 +252,22 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
             }
         }
         __syncthreads();
-        // check nodes: one (check, output edge) task per thread, shared-memory chunk by chunk
-        const int tasks = M * p.dc_max;
-        for (int base = 0; base < tasks; base += p.ems_chunk) {
-            const int t = base + tid;
-            if (tid < p.ems_chunk && t < tasks) {
-                const int row = t / p.dc_max, dc = t - row * p.dc_max;
-                if (dc < p.cw[row]) ems_check_task(p, row, dc, v2c, topsym, topval, c2v, smemE + tid, p.ems_chunk);
+        // check nodes: one (check, output edge) task per warp, E[q] of the warp in shared memory
+        const int tasks = M * p.dc_max, warp = tid >> 5, nwarps = T >> 5;
+        for (int t = warp; t < tasks; t += nwarps) {
+            const int row = t / p.dc_max, dc = t - row * p.dc_max;
+            if (dc < p.cw[row]) {
+                float *base = smemE + (size_t)warp * ems_warp_floats(q);
+                EmsWarpShared ws;
+                ws.E = base;
+                ws.ie = reinterpret_cast<int *>(base + q);
+                ws.ih = ws.ie + 32;
+                ws.tval = base + q + 64;
+                ws.tsym = reinterpret_cast<int *>(ws.tval + 32 * kNmMax);
+                ems_check_task_warp(p, row, dc, v2c, topsym, topval, c2v, ws, tid & 31);
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
     if (tid == 0) {
         if (p.iters_out) p.iters_out[f] = it;
@@ -648,9 +686,8 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     size_t smem = 0;
     int ems_chunk = 0;
     if (o->algo == NB_ALGO_EMS) {
-        ems_chunk = kNbThreads;
-        while ((size_t)ems_chunk * q * sizeof(float) > 200 * 1024) ems_chunk /= 2;
-        smem = (size_t)ems_chunk * q * sizeof(float);
+        ems_chunk = kNbThreads / 32;
+        smem = (size_t)ems_chunk * ems_warp_floats(q) * sizeof(float);  // E[q] + input lists per warp
     } else if (o->algo == NB_ALGO_FFT_BP) {
         if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;
         for (int g : c->c_gf)
