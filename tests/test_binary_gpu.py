@@ -249,3 +249,43 @@ def test_layered_fp32_bit_exact_vs_oracle(oracle, key, F, snr, alpha, mode):
     D, it, app = orc_l32(oracle, oc, y, 8, mode, alpha)
     assert (r.iters == it).all() and (r.D == D).all()
     assert (r.app.view(np.uint32) == app.view(np.uint32)).all()
+
+
+def test_full_size_roundtrip_properties(oracle):
+    """BASELINE.json's full size (J15_L30_Z1280, 9472 frames per GPU per step, as in bench.py), checked
+    through size-independent properties: encode -> AWGN -> decode returns the transmitted codeword for
+    every frame flagged ok; the flag equals an independent syndrome computation; permuting the frames
+    permutes the results; the fused-channel path and the buffer path agree on the whole batch."""
+    import torch
+    code, oc = load(oracle, "C2")
+    F = 148 * 4 * 16
+    u = np.random.default_rng(11).integers(0, 2, code.K).astype(np.uint8)
+    cw = np.zeros(code.N, np.uint8)
+    assert m.lib.ldpc_encode(code.handle, u.ctypes.data, cw.ctypes.data) == 0
+    cwd = torch.as_tensor(cw, device="cuda")
+    sigma = m.sigma_from_snr(0, 2.4, code.rate)
+    y = torch.empty(code.N * F, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert m.lib.ldpc_awgn_bpsk(code.handle, y.data_ptr(), F, m.LAYOUT_NF, sigma, 5, 0, cwd.data_ptr(), st) >= 0
+    y = y.view(code.N, F)
+    kw = dict(early_exit=m.EXIT_SYNDROME, out_format=m.OUT_U8, msg_max=31, beta_num=1, beta_shift=3)
+    r = code.decode(y, 10, schedule=m.SCHED_LAYERED, **kw)
+    ok = r.ok.bool()
+    assert ok.float().mean() > 0.99
+    assert (r.D[:, ok] == cwd[:, None]).all()                       # decoded = transmitted
+    # syndrome of every decoded word, computed independently on the GPU with torch
+    H = oc.H.reshape(oc.J, oc.L)
+    D = r.D.view(oc.L, oc.Z, F)
+    syn_bad = torch.zeros(F, dtype=torch.bool, device="cuda")
+    for rr in range(oc.J):
+        acc = torch.zeros(oc.Z, F, dtype=torch.uint8, device="cuda")
+        for c in range(oc.L):
+            if H[rr, c] >= 0:
+                acc ^= torch.roll(D[c], -int(H[rr, c]), 0)         # row i reads column (i + s) mod Z
+        syn_bad |= (acc != 0).any(0)
+    assert (syn_bad == ~ok).all()
+    perm = torch.randperm(F, device="cuda")
+    rp = code.decode(y[:, perm].contiguous(), 10, schedule=m.SCHED_LAYERED, **kw)
+    assert (rp.D == r.D[:, perm]).all() and (rp.iters == r.iters[perm]).all()
+    rf = code.decode_channel(F, 10, sigma, seed=5, first_frame=0, codeword=cwd, **kw)
+    assert (rf.D == r.D).all() and (rf.iters == r.iters).all() and (rf.ok == r.ok).all()
