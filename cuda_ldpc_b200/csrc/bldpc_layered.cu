@@ -6,9 +6,10 @@
 //    only the channel values in and the hard decisions out;
 //  * thread = check row i of the current layer (block row of H); the circulant shift is the
 //    shared-memory address (i + s) mod Z, consecutive threads hit consecutive banks;
-//  * arithmetic is 2-way SIMD on half2 lanes holding small integers (|x| <= 254 is exact in
-//    fp16): HADD2 / HMNMX2 / HSET2.BM / LOP3 / PRMT — sm_100a has no native 8x4 SIMD
-//    integer min/compare (the __v*4 intrinsics expand to 5-10 instructions, profiles/r01_simd_sass.txt);
+//  * arithmetic is 2-way SIMD on half2 lanes holding small integers (exact in fp16 below 2048):
+//    HADD2 / HFMA2 / HSET2 / PRMT / LOP3 plus the 16x2 integer min/max family on fp16 bit patterns
+//    (VIMNMX.U16x2, VIMNMX3.U16x2, VIADDMNMX.S16x2.RELU) — sm_100a has no native 8x4 SIMD integer
+//    min/compare (the __v*4 intrinsics expand to 5-10 instructions, profiles/r01_simd_sass.txt);
 //  * the compressed check record {min1, min2, idx, sign bits} is streamed through a per-CTA
 //    slice of a scratch buffer that stays L2-resident (148 CTAs x M x 32 B << 126 MB);
 //  * the syndrome (early exit / ok flag) is a cheap extra pass: XOR of the sign bits.
@@ -43,8 +44,8 @@ struct LayeredParams {
     unsigned long long ch_first;
     const unsigned char *ch_cw;
     int scale_on;           // beta_num != 0
-    unsigned c64;           // 0x64646464: kept in a register so PRMT can take the selector as its immediate
-    // kernel-ready layer tables: entry e = {column-block byte offset c*Z*4, shift byte offset s*4}
+    unsigned c65;           // 0x65656565: kept in a register so PRMT can take the selector as its immediate
+    // kernel-ready layer tables: entry e = {byte offset (c*Z + s)*4 of row 0's bit, wrap threshold (Z - s)*4}
     int2 tab[kMaxBlocks];
     unsigned short off[kMaxLayers];
     unsigned char dc[kMaxLayers];
@@ -110,21 +111,6 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned s)
 }
 __device__ __forceinline__ unsigned sel(unsigned mask, unsigned a, unsigned b) { return (a & mask) | (b & ~mask); }
 
-// biased uint8 x4  ->  half2 lanes (frames 0,1) / (frames 2,3): 0x6400|b is 1024+b in fp16
-__device__ __forceinline__ __half2 unpack_lo(unsigned w)
-{
-    return __hsub2(u2h(prmt(w, 0x64646464u, 0x4140u)), __float2half2_rn(1152.0f));
-}
-__device__ __forceinline__ __half2 unpack_hi(unsigned w)
-{
-    return __hsub2(u2h(prmt(w, 0x64646464u, 0x4342u)), __float2half2_rn(1152.0f));
-}
-__device__ __forceinline__ unsigned pack4(__half2 a, __half2 b)
-{
-    const __half2 k = __float2half2_rn(1152.0f);
-    return prmt(h2u(__hadd2(a, k)), h2u(__hadd2(b, k)), 0x6420u);
-}
-
 __device__ __forceinline__ int quant(float y, float scale)
 {
     int q = __float2int_rn(__fmul_rn(y, scale));
@@ -164,25 +150,57 @@ __host__ __device__ constexpr int sign_bit_pos(int dc, int k)
 // a constant-bank load at an immediate offset, every shift amount is an immediate).  !EXACT: DC is
 // the bucket's maximum and edges k >= dc are predicated off (rare degrees only).
 //
-// Pipe balance (ncu: the ALU pipe is the binding one, profiles/r01_*): selects, index tracking and
-// the sign/parity collection run as HFMA2 / HADD2 / HSET2.BF on the FMA pipe; only the byte
-// shuffles (PRMT), the sign XORs (LOP3) and the fp16 min/max (HMNMX2) stay on the ALU pipe.
-//
-// Works on t' = t + 1152 so that the re-biasing add of the store path disappears:
-//   a' = 1152 + APP (the PRMT result read as fp16),  t' = a' - c2v_old,  t = t' - 1152,
-//   APP'_biased_fp16 = clamp(t' + c2v_new, 1025, 1279).
+// Number formats (all exact):
+//  * smem byte b = APP + 127 (0..254).  PRMT with the constant byte 0x65 turns it into the fp16 pattern
+//    0x6500|b = 1280 + b = APP + 1407; t' = t + 1407 then stays inside the binade [1024, 2048) for every
+//    reachable t (|t| <= 254) and so does t' + c2v_new, where an fp16 pattern is 0x6400 + (value - 1024):
+//    the final "add, clamp to [-127,127], re-bias" is ONE integer SIMD instruction on the pattern,
+//    VIADDMNMX.S16x2.RELU: max(min(pattern - 0x6500, 254), 0) = clamp(APP_new) + 127.
+//  * min1 / min2 / first index are tracked on keys |t|*8 + (k mod 8) (< 2048, exact in fp16; positive
+//    fp16 patterns order like unsigned integers, so VIMNMX(3).U16x2 does the comparisons), one
+//    accumulator pair per set of 8 edges; the amax clamp commutes with the minimum and is applied to
+//    the keys once per row (key1 -> min(key1, 8*amax) also yields the oracle's "first index" when every
+//    |t| saturates).  Keys are decoded (floor(key/8), key mod 8) on the FMA pipe.
+//  * sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)), (t<0) = fma.sat(t, -1, 0).
+// Pipe balance (ncu: the ALU pipe was the binding one, profiles/r01_*): per edge and pair of frames the
+// ALU pipe sees PRMT, HSET2.EQ, LOP3, 2.5 x VIMNMX in phase 1 and HSET2.EQ, LOP3, VIADDMNMX in phase 2;
+// everything else (selects, sign/parity collection, keys, decode, beta scaling) is HFMA2 / HADD2 / IMAD.
+__device__ __forceinline__ __half2 neg01(__half2 t)
+{
+    unsigned d;
+    asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(h2u(t)), "r"(0xBC00BC00u), "r"(0u));
+    return u2h(d);
+}
+__device__ __forceinline__ __half2 umin2(__half2 a, __half2 b) { return u2h(__vminu2(h2u(a), h2u(b))); }
+__device__ __forceinline__ __half2 umax2(__half2 a, __half2 b) { return u2h(__vmaxu2(h2u(a), h2u(b))); }
+__device__ __forceinline__ __half2 umin3(__half2 a, __half2 b, __half2 c)
+{
+    return u2h(__vimin3_u16x2(h2u(a), h2u(b), h2u(c)));
+}
+// floor(c / 8) for integer-valued 0 <= c <= 1023: c/8 - 7/16 has at most 11 significant bits, and adding
+// 1025 (ulp 1, never a tie) rounds it to 1025 + floor
+__device__ __forceinline__ __half2 floor8(__half2 c)
+{
+    const __half2 k = __float2half2_rn(1025.0f);
+    const __half2 u = __hfma2(c, __float2half2_rn(0.125f), __float2half2_rn(-0.4375f));
+    return __hsub2(__hadd2(u, k), k);
+}
+
 template <int DC, int DCHI, bool FIRST, bool EXACT>
-__device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParams &p, int off, int dc_rt, int i4,
-                                              int Z4, uint4 *recp, __half2 amax, __half2 bmul, __half2 nbias)
+__device__ __forceinline__ void process_row_x(unsigned isb, int i4, const LayeredParams &p, int off, int dc_rt,
+                                              int Z4, uint4 *recp, __half2 amax8, __half2 amax8p7, __half2 bmul,
+                                              __half2 nbias)
 {
     constexpr int SW = RecLayout<DCHI>::SW;  // record layout of the kernel's degree bucket
     constexpr int U4 = RecLayout<DCHI>::U4;
+    constexpr int NS = (DC + 7) / 8;         // key sets
     const int dc = EXACT ? DC : dc_rt;
     unsigned rw[U4 * 4];
     if (!FIRST) rec_load<U4>(recp, rw);
     // record words: [0,1] m1 (frames 01, 23)  [2,3] m2  [4,5] idx  [6 + h*SW + g] sign words
-    const __half2 k1152 = __float2half2_rn(1152.0f), k1024 = __float2half2_rn(1024.0f);
-    const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f);
+    const __half2 kbias = __float2half2_rn(1407.0f), k1024 = __float2half2_rn(1024.0f);
+    const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f), eight = __float2half2_rn(8.0f);
+    const __half2 sent = __float2half2_rn(2047.0f);
     __half2 dold[2];
     if (!FIRST) {
         dold[0] = __hsub2(u2h(rw[2]), u2h(rw[0]));
@@ -190,53 +208,92 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
     }
     unsigned addr[DC];
     __half2 tp[2][DC];
-    __half2 min1[2] = {amax, amax}, min2[2] = {amax, amax};
-    __half2 idx[2] = {zero, zero}, cnt[2] = {zero, zero};
+    __half2 k1[2][NS], k2[2][NS], kprev[2];
+    __half2 cnt[2] = {zero, zero};
     __half2 sacc[2][SW];
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < 2; h++) {
 #pragma unroll
         for (int g = 0; g < SW; g++) sacc[h][g] = zero;
 #pragma unroll
+        for (int s = 0; s < NS; s++) k1[h][s] = k2[h][s] = sent;
+    }
+#pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
-            const __half2 kh = __float2half2_rn((float)k);
-            const int2 e = p.tab[off + k];
-            int col4 = i4 + e.y;
-            col4 -= (col4 >= Z4) ? Z4 : 0;
-            addr[k] = sbase + (unsigned)(e.x + col4);
-            const unsigned wk = lds32(addr[k]);
+            const int s = k >> 3, kl = k & 7;
+            const __half2 kh = __float2half2_rn((float)k), klh = __float2half2_rn((float)kl);
+            const int2 e = p.tab[off + k];  // {column-block base + shift (bytes), wrap threshold (Z - s) * 4}
+            unsigned a = isb + (unsigned)e.x;
+            a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+            addr[k] = a;
+            const unsigned wk = lds32(a);
             const int sh = 15 - sign_bit_pos(dc, k);  // brings edge k's sign bit to bit 15 of each lane
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                __half2 t1 = u2h(prmt(wk, p.c64, h ? 0x4342u : 0x4140u));
+                __half2 t1 = u2h(prmt(wk, p.c65, h ? 0x4342u : 0x4140u));
                 if (!FIRST) {
                     const __half2 mag = __hfma2(__heq2(u2h(rw[4 + h]), kh), dold[h], u2h(rw[h]));
                     const unsigned sg = (rw[6 + h * SW + k / kSignGroup] << sh) & 0x80008000u;
                     t1 = __hsub2(t1, u2h(h2u(mag) ^ sg));
                 }
                 tp[h][k] = t1;
-                const __half2 tt = __hsub2(t1, k1152);
-                const __half2 ab = __hmin2(__habs2(tt), amax);
-                const __half2 neg = __hlt2(tt, zero);  // 1.0 where t < 0 (t is never -0)
+                const __half2 tt = __hsub2(t1, kbias);
+                const __half2 neg = neg01(tt);  // 1.0 where t < 0
                 sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
                 cnt[h] = __hadd2(cnt[h], neg);
-                const __half2 lt = __hlt2(ab, min1[h]);
-                idx[h] = __hfma2(lt, __hsub2(kh, idx[h]), idx[h]);
-                min2[h] = __hmin2(min2[h], __hmax2(min1[h], ab));
-                min1[h] = __hmin2(min1[h], ab);
+                const __half2 key = __hfma2(__habs2(tt), eight, klh);
+                if (!EXACT) {
+                    k2[h][s] = umin2(k2[h][s], umax2(k1[h][s], key));
+                    k1[h][s] = umin2(k1[h][s], key);
+                } else if ((kl & 1) == 0) {
+                    if (k == DC - 1) {  // unpaired last edge
+                        k2[h][s] = umin2(k2[h][s], umax2(k1[h][s], key));
+                        k1[h][s] = umin2(k1[h][s], key);
+                    } else {
+                        kprev[h] = key;
+                    }
+                } else {  // pair (k-1, k): 5 min/max for two edges, 2 for the first pair of a set
+                    const __half2 lo = umin2(kprev[h], key), hi = umax2(kprev[h], key);
+                    if (kl == 1) {
+                        k1[h][s] = lo;
+                        k2[h][s] = hi;
+                    } else {
+                        k2[h][s] = umin3(k2[h][s], hi, umax2(k1[h][s], lo));
+                        k1[h][s] = umin2(k1[h][s], lo);
+                    }
+                }
             }
         }
     }
     unsigned nsg[2][SW];
-    __half2 dnew[2];
+    __half2 min1[2], idx[2], dnew[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        if (p.scale_on) {
-            min1[h] = beta_scale(min1[h], bmul, nbias);
-            min2[h] = beta_scale(min2[h], bmul, nbias);
+        __half2 m1 = zero, m2 = zero, ix = zero;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const __half2 c1 = umin2(k1[h][s], amax8), c2 = umin2(k2[h][s], amax8p7);
+            const __half2 a1 = floor8(c1), a2 = floor8(c2);
+            const __half2 ia = __hfma2(a1, __float2half2_rn(-8.0f), c1);
+            if (s == 0) {
+                m1 = a1;
+                m2 = a2;
+                ix = ia;
+            } else {  // strict "<": the earlier set keeps the index on equal minima (first index)
+                const __half2 lt = __hlt2(a1, m1);
+                ix = __hfma2(lt, __hsub2(__hadd2(ia, __float2half2_rn(8.0f * s)), ix), ix);
+                m2 = umin2(umax2(m1, a1), umin2(m2, a2));
+                m1 = umin2(m1, a1);
+            }
         }
-        dnew[h] = __hsub2(min2[h], min1[h]);
+        if (p.scale_on) {
+            m1 = beta_scale(m1, bmul, nbias);
+            m2 = beta_scale(m2, bmul, nbias);
+        }
+        min1[h] = m1;
+        idx[h] = ix;
+        dnew[h] = __hsub2(m2, m1);
         // parity of the negative-sign count -> 0xFFFF per lane; sign bits of all dc edges flip with it
         const unsigned pm = (h2u(__hadd2(cnt[h], k1024)) & 0x00010001u) * 0xFFFFu;
 #pragma unroll
@@ -246,15 +303,14 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
             const unsigned gm = ((1u << gs) - 1u) * 0x00010001u;
             nsg[h][g] = (h2u(__hadd2(sacc[h][g], k1024)) ^ pm) & gm;
         }
-        rw[h] = h2u(min1[h]);
-        rw[2 + h] = h2u(min2[h]);
-        rw[4 + h] = h2u(idx[h]);
+        rw[h] = h2u(m1);
+        rw[2 + h] = h2u(m2);
+        rw[4 + h] = h2u(ix);
 #pragma unroll
         for (int g = 0; g < SW; g++) rw[6 + h * SW + g] = nsg[h][g];
     }
     rec_store<U4>(recp, rw);
 
-    const __half2 hi = __float2half2_rn(1279.0f), lo = __float2half2_rn(1025.0f);
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
@@ -266,7 +322,8 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
                 const __half2 mag = __hfma2(__heq2(idx[h], kh), dnew[h], min1[h]);
                 const unsigned sg = (nsg[h][k / kSignGroup] << sh) & 0x80008000u;
                 const __half2 x = __hadd2(tp[h][k], u2h(h2u(mag) ^ sg));
-                v[h] = h2u(__hmin2(__hmax2(x, lo), hi));
+                // pattern(x) = 0x6400 + (APP_new + 383): subtract 0x6500, clamp to [0, 254]
+                v[h] = __viaddmin_s16x2_relu(h2u(x), 0x9B009B00u, 0x00FE00FEu);
             }
             sts32(addr[k], prmt(v[0], v[1], 0x6420u));
         }
@@ -277,18 +334,19 @@ __device__ __forceinline__ void process_row_x(unsigned sbase, const LayeredParam
 // that its register needs do not leak into the allocation of the hot exact-degree paths.
 template <int DCHI, bool FIRST>
 __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *recl,
-                                          __half2 amax, __half2 bmul, __half2 nbias)
+                                          __half2 amax8, __half2 amax8p7, __half2 bmul, __half2 nbias)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
     const int Z = p.Z, Z4 = 4 * Z;
     for (int i = threadIdx.x; i < Z; i += blockDim.x)
-        process_row_x<DCHI, DCHI, FIRST, false>(sbase, p, off, dc, 4 * i, Z4, recl + (size_t)i * RS, amax, bmul, nbias);
+        process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RS, amax8,
+                                                amax8p7, bmul, nbias);
 }
 
 // One full iteration: all layers in order, the Z rows of a layer spread over the CTA.
 template <int DCHI, bool FIRST>
-__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec,
-                                             __half2 amax, __half2 bmul, __half2 nbias)
+__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec, __half2 amax8,
+                                             __half2 amax8p7, __half2 bmul, __half2 nbias)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
     const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
@@ -306,7 +364,8 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         }
 #define LDPC_ROWS(DCX)                                                                                        \
     for (int i = tid; i < Z; i += T)                                                                          \
-        process_row_x<DCX, DCHI, FIRST, true>(sbase, p, off, DCX, 4 * i, Z4, recl + (size_t)i * RS, amax, bmul, nbias);
+        process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * RS, amax8, \
+                                              amax8p7, bmul, nbias);
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
         } else if (DCHI >= 2 && dc == DCHI - 1) {
@@ -316,7 +375,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         } else if (DCHI >= 4 && dc == DCHI - 3) {
             LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
-            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amax, bmul, nbias);
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amax8, amax8p7, bmul, nbias);
         }
 #undef LDPC_ROWS
         __syncthreads();
@@ -327,12 +386,12 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
 __device__ __forceinline__ unsigned syndrome_row(const unsigned char *app, const LayeredParams &p, int off, int dc,
                                                  int i4, int Z4)
 {
-    unsigned x = (dc & 1) ? 0x80808080u : 0u;  // biased byte: negative <=> bit7 clear
+    unsigned x = (dc & 1) ? 0x80808080u : 0u;  // byte = APP + 127 (<= 254): negative <=> bit 7 of byte + 1 clear
     for (int k = 0; k < dc; k++) {
         const int e = off + k;
         int col4 = i4 + 4 * (int)p.lt.shift[e];
         col4 -= (col4 >= Z4) ? Z4 : 0;
-        x ^= *reinterpret_cast<const unsigned *>(app + (int)p.lt.col[e] * Z4 + col4);
+        x ^= *reinterpret_cast<const unsigned *>(app + (int)p.lt.col[e] * Z4 + col4) + 0x01010101u;
     }
     return x & 0x80808080u;
 }
@@ -343,8 +402,8 @@ __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int 
     const int F = p.F, N = p.N, f0 = 4 * g;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const unsigned w = appw[n];
-        // bit j of `bits` = hard decision of frame j (biased byte < 128)
-        const unsigned nb = ~w;
+        // bit j of `bits` = hard decision of frame j (APP < 0 <=> byte + 1 < 128; bytes never exceed 254)
+        const unsigned nb = ~(w + 0x01010101u);
         const unsigned bits = ((nb >> 7) & 1u) | ((nb >> 14) & 2u) | ((nb >> 21) & 4u) | ((nb >> 28) & 8u);
         if (p.out_format == LDPC_OUT_INT32_REF) {
             int *D = reinterpret_cast<int *>(p.out);
@@ -363,7 +422,7 @@ __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int 
         if (p.dbg_app) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                if ((fmask >> j) & 1u) p.dbg_app[(size_t)n * F + f0 + j] = (signed char)((int)((w >> (8 * j)) & 255u) - 128);
+                if ((fmask >> j) & 1u) p.dbg_app[(size_t)n * F + f0 + j] = (signed char)((int)((w >> (8 * j)) & 255u) - 127);
         }
     }
     if (p.out_format == LDPC_OUT_BITPACK) {
@@ -372,7 +431,7 @@ __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int 
         const int lane = threadIdx.x & 31;
         const int nround = (N + 31) & ~31;
         for (int n = threadIdx.x; n < nround; n += blockDim.x) {  // blockDim is a multiple of 32
-            const unsigned w = (n < N) ? appw[n] : 0x80808080u;
+            const unsigned w = (n < N) ? appw[n] + 0x01010101u : 0x80808080u;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const unsigned b = __ballot_sync(0xffffffffu, ((w >> (8 * j + 7)) & 1u) == 0u);
@@ -426,7 +485,8 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     const int N = p.N, Z = p.Z, F = p.F, Z4 = 4 * Z;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * RecLayout<DCMAX>::STRIDE;
-    const __half2 amax = __float2half2_rn(p.msg_max);
+    const __half2 amax8 = __float2half2_rn(8.0f * p.msg_max);  // key clamps: min1 -> 8*amax, min2 -> 8*amax + 7
+    const __half2 amax8p7 = __float2half2_rn(8.0f * p.msg_max + 7.0f);
     const __half2 bmul = __float2half2_rn(p.beta_mul);
     const __half2 nbias = __float2half2_rn(-p.beta_bias);
 
@@ -463,13 +523,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int q = ((valid >> j) & 1u) ? quant(awgn_bpsk_sample(bit, p.ch_sigma, g[j][b]), p.scale) : 127;
-                        w |= (unsigned)(q + 128) << (8 * j);
+                        w |= (unsigned)(q + 127) << (8 * j);
                     }
                     appw[n] = w;
                 }
             }
         }
-        // ---- load + quantise: q = sat127(rint(y * scale)), stored biased by 128
+        // ---- load + quantise: q = sat127(rint(y * scale)), stored biased by 127
 #pragma unroll 4
         for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL) ? N : tid; n < N; n += T) {
             int q[4];
@@ -503,8 +563,8 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                     q[j] = ((valid >> j) & 1u) ? max(-127, (int)y[o]) : 127;
                 }
             }
-            appw[n] = (unsigned)(q[0] + 128) | ((unsigned)(q[1] + 128) << 8) | ((unsigned)(q[2] + 128) << 16) |
-                      ((unsigned)(q[3] + 128) << 24);
+            appw[n] = (unsigned)(q[0] + 127) | ((unsigned)(q[1] + 127) << 8) | ((unsigned)(q[2] + 127) << 16) |
+                      ((unsigned)(q[3] + 127) << 24);
         }
         if (tid == 0) s_fail = 0u;
         __syncthreads();
@@ -520,9 +580,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         while (it < p.iters) {
             it++;
             if (it == 1)
-                sweep_layers<DCMAX, true>(sbase, p, rec, amax, bmul, nbias);
+                sweep_layers<DCMAX, true>(sbase, p, rec, amax8, amax8p7, bmul, nbias);
             else
-                sweep_layers<DCMAX, false>(sbase, p, rec, amax, bmul, nbias);
+                sweep_layers<DCMAX, false>(sbase, p, rec, amax8, amax8p7, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 unsigned fail = 0u;
                 for (int r = 0; r < p.J; r++) {
@@ -666,14 +726,14 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.ch_first = a.ch_first;
     p.ch_cw = a.ch_cw;
     p.scale_on = a.beta_num != 0;
-    p.c64 = 0x64646464u;
+    p.c65 = 0x65656565u;
     p.lt = c->lt;
     for (int r = 0; r < c->J; r++) {
         p.off[r] = c->lt.off[r];
         p.dc[r] = c->lt.dc[r];
         for (int k = 0; k < c->lt.dc[r]; k++) {
             const int e = c->lt.off[r] + k;
-            p.tab[e] = make_int2((int)c->lt.col[e] * c->Z * 4, (int)c->lt.shift[e] * 4);
+            p.tab[e] = make_int2(((int)c->lt.col[e] * c->Z + (int)c->lt.shift[e]) * 4, (c->Z - (int)c->lt.shift[e]) * 4);
         }
     }
     switch (pl.dcb) {
