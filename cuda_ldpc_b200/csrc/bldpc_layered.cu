@@ -22,6 +22,18 @@
 #include "common.h"
 #include "philox.cuh"
 
+// tuning switches (A/B-tested on B200, tools/ab): depth of the channel-value load batch, step-ahead L1
+// prefetch of the check records, L2 prefetch of the next group's channel values (off: it evicted records)
+#ifndef LDPC_L2_PREFETCH
+#define LDPC_L2_PREFETCH 0
+#endif
+#ifndef LDPC_REC_PREFETCH
+#define LDPC_REC_PREFETCH 1
+#endif
+#ifndef LDPC_LOAD_DEPTH
+#define LDPC_LOAD_DEPTH 8
+#endif
+
 namespace ldpcb {
 
 struct LayeredParams {
@@ -330,42 +342,61 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
     }
 }
 
+// The record a thread needs in its NEXT step (its next row of this layer, else its first row of the next
+// layer / next iteration) is pulled into L1 one step ahead.  One step is ~2 us of lead (L2 or HBM latency is
+// covered) and only two steps of records (2 x T x 32..64 B) compete for the L1 space left beside the APP
+// words; prefetching a whole layer ahead (80 KB in flight for J15_L30_Z1280 against ~73 KB of L1) lost most
+// lines before their use (ncu: 26 % of the stall samples were long-scoreboard waits on the record load).
+template <int DCHI, bool FIRST>
+__device__ __forceinline__ void prefetch_next_record(const uint4 *recl, const uint4 *nxl, int i, int T, int Z,
+                                                     bool pf_next_layer)
+{
+    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    if (!LDPC_REC_PREFETCH) return;
+    const bool same_layer = i + T < Z;
+    const uint4 *nx = same_layer ? recl + (size_t)(i + T) * RS : nxl + (size_t)threadIdx.x * RS;
+    if (same_layer ? !FIRST : pf_next_layer) {
+        prefetch_l1(nx);
+        if (RecLayout<DCHI>::U4 > 2) prefetch_l1(nx + 2);
+    }
+}
+
 // Rows of a layer whose degree is outside the exact range of the kernel's bucket.  Out of line so
 // that its register needs do not leak into the allocation of the hot exact-degree paths.
 template <int DCHI, bool FIRST>
 __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *recl,
-                                          __half2 amax8, __half2 amax8p7, __half2 bmul, __half2 nbias)
+                                          const uint4 *nxl, bool pf_next_layer, __half2 amax8, __half2 amax8p7,
+                                          __half2 bmul, __half2 nbias)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
-    const int Z = p.Z, Z4 = 4 * Z;
-    for (int i = threadIdx.x; i < Z; i += blockDim.x)
+    const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
+    for (int i = threadIdx.x; i < Z; i += T) {
+        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer);
         process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RS, amax8,
                                                 amax8p7, bmul, nbias);
+    }
 }
 
 // One full iteration: all layers in order, the Z rows of a layer spread over the CTA.
 template <int DCHI, bool FIRST>
-__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec, __half2 amax8,
-                                             __half2 amax8p7, __half2 bmul, __half2 nbias)
+__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec, bool last,
+                                             __half2 amax8, __half2 amax8p7, __half2 bmul, __half2 nbias)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
     const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
     for (int r = 0; r < p.J; r++) {
         const int dc = p.dc[r], off = p.off[r];
         uint4 *recl = rec + (size_t)r * Z * RS;
-        // the records of the NEXT layer (next iteration's first layer after the last one) are read a
-        // whole layer from now: pull them into L1 so the row loop never waits on L2/HBM
-        if (!FIRST || r == p.J - 1) {
-            const uint4 *nxt = rec + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
-            for (int i = tid; i < Z; i += T) {
-                prefetch_l1(nxt + (size_t)i * RS);
-                if (RecLayout<DCHI>::U4 > 2) prefetch_l1(nxt + (size_t)i * RS + 2);
-            }
-        }
+        // this thread's first row of the next layer (of the next iteration after the last layer); it is
+        // prefetched only if a sweep that reads records follows
+        const uint4 *nxl = rec + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
+        const bool pf_next_layer = (!FIRST || r == p.J - 1) && !(last && r == p.J - 1);
 #define LDPC_ROWS(DCX)                                                                                        \
-    for (int i = tid; i < Z; i += T)                                                                          \
+    for (int i = tid; i < Z; i += T) {                                                                        \
+        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer);                                 \
         process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * RS, amax8, \
-                                              amax8p7, bmul, nbias);
+                                              amax8p7, bmul, nbias);                                          \
+    }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
         } else if (DCHI >= 2 && dc == DCHI - 1) {
@@ -375,7 +406,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         } else if (DCHI >= 4 && dc == DCHI - 3) {
             LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
-            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amax8, amax8p7, bmul, nbias);
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, nxl, pf_next_layer, amax8, amax8p7, bmul, nbias);
         }
 #undef LDPC_ROWS
         __syncthreads();
@@ -530,8 +561,32 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             }
         }
         // ---- load + quantise: q = sat127(rint(y * scale)), stored biased by 127
-#pragma unroll 4
-        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL) ? N : tid; n < N; n += T) {
+        // fp32 [N][F], whole group: one 16-byte vector per code bit, LDPC_LOAD_DEPTH loads in flight per thread
+        const bool fast_load = LDPC_LOAD_DEPTH > 1 && p.llr_dtype == LDPC_DTYPE_FP32 && p.layout == LDPC_LAYOUT_NF &&
+                               valid == 0xFu && (F & 3) == 0;
+        if (fast_load) {
+            constexpr int kLoadDepth = LDPC_LOAD_DEPTH;
+            const float4 *y4 = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.llr) + f0);
+            const size_t st4 = (size_t)(F >> 2);
+            for (int n0 = tid; n0 < N; n0 += kLoadDepth * T) {
+                float4 v[kLoadDepth];
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) {  // tail: re-read the last bit instead of predicating
+                    const int n = min(n0 + u * T, N - 1);
+                    v[u] = __ldg(y4 + (size_t)n * st4);
+                }
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) {
+                    const int n = n0 + u * T;
+                    if (n < N)
+                        appw[n] = (unsigned)(quant(v[u].x, p.scale) + 127) | ((unsigned)(quant(v[u].y, p.scale) + 127) << 8) |
+                                  ((unsigned)(quant(v[u].z, p.scale) + 127) << 16) |
+                                  ((unsigned)(quant(v[u].w, p.scale) + 127) << 24);
+                }
+            }
+        }
+#pragma unroll 2
+        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL || fast_load) ? N : tid; n < N; n += T) {
             int q[4];
             if (p.llr_dtype == LDPC_DTYPE_FP32) {
                 const float *y = reinterpret_cast<const float *>(p.llr);
@@ -569,7 +624,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         if (tid == 0) s_fail = 0u;
         __syncthreads();
         // pull the channel values of this CTA's next group towards L2 while this group is decoded
-        if (!dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
+        if (LDPC_L2_PREFETCH && !dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
             p.layout == LDPC_LAYOUT_NF) {
             const float *y = reinterpret_cast<const float *>(p.llr) + 4 * (size_t)(g + gridDim.x);
             for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
@@ -580,9 +635,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         while (it < p.iters) {
             it++;
             if (it == 1)
-                sweep_layers<DCMAX, true>(sbase, p, rec, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, amax8, amax8p7, bmul, nbias);
             else
-                sweep_layers<DCMAX, false>(sbase, p, rec, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, amax8, amax8p7, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 unsigned fail = 0u;
                 for (int r = 0; r < p.J; r++) {
