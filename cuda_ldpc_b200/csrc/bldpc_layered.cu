@@ -22,13 +22,24 @@
 #include "common.h"
 #include "philox.cuh"
 
-// tuning switches (A/B-tested on B200, tools/ab): depth of the channel-value load batch, step-ahead L1
-// prefetch of the check records, L2 prefetch of the next group's channel values (off: it evicted records)
+// Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it):
+//   LDPC_REC_PRELOAD   1  the record of a thread's next step is loaded into registers between the two phases
+//                         of the current row (9.07 -> 8.70 ms; an L1 or L2 prefetch on top of it LOSES 2 %)
+//   LDPC_REC_PREFETCH  0  1 = prefetch.global.L1, 2 = prefetch.global.L2 of the next step's record at row start
+//   LDPC_PARITY_XOR    1  sign parity as xor of the t patterns (LOP3) instead of an fp16 count (9.30 -> 9.06 ms)
+//   LDPC_LOAD_DEPTH    8  channel-value vectors in flight per thread in the load phase
+//   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values (on: evicts records, +4 %)
 #ifndef LDPC_L2_PREFETCH
 #define LDPC_L2_PREFETCH 0
 #endif
 #ifndef LDPC_REC_PREFETCH
-#define LDPC_REC_PREFETCH 1
+#define LDPC_REC_PREFETCH 0
+#endif
+#ifndef LDPC_PARITY_XOR
+#define LDPC_PARITY_XOR 1
+#endif
+#ifndef LDPC_REC_PRELOAD
+#define LDPC_REC_PRELOAD 1
 #endif
 #ifndef LDPC_LOAD_DEPTH
 #define LDPC_LOAD_DEPTH 8
@@ -198,17 +209,20 @@ __device__ __forceinline__ __half2 floor8(__half2 c)
     return __hsub2(__hadd2(u, k), k);
 }
 
+// Record flow: `rw` holds this row's record on entry (!FIRST) and the record of the thread's NEXT step on
+// exit (`ld_next`: the load is issued between the two phases, so its latency hides under phase 2; the
+// registers of the old record are dead by then).
 template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const LayeredParams &p, int off, int dc_rt,
-                                              int Z4, uint4 *recp, __half2 amax8, __half2 amax8p7, __half2 bmul,
-                                              __half2 nbias)
+                                              int Z4, uint4 *recp, const uint4 *nx, bool ld_next,
+                                              unsigned (&rw)[RecLayout<DCHI>::U4 * 4], __half2 amax8,
+                                              __half2 amax8p7, __half2 bmul, __half2 nbias)
 {
     constexpr int SW = RecLayout<DCHI>::SW;  // record layout of the kernel's degree bucket
     constexpr int U4 = RecLayout<DCHI>::U4;
     constexpr int NS = (DC + 7) / 8;         // key sets
     const int dc = EXACT ? DC : dc_rt;
-    unsigned rw[U4 * 4];
-    if (!FIRST) rec_load<U4>(recp, rw);
+    if (!FIRST && !LDPC_REC_PRELOAD) rec_load<U4>(recp, rw);
     // record words: [0,1] m1 (frames 01, 23)  [2,3] m2  [4,5] idx  [6 + h*SW + g] sign words
     const __half2 kbias = __float2half2_rn(1407.0f), k1024 = __float2half2_rn(1024.0f);
     const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f), eight = __float2half2_rn(8.0f);
@@ -221,7 +235,8 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
     unsigned addr[DC];
     __half2 tp[2][DC];
     __half2 k1[2][NS], k2[2][NS], kprev[2];
-    __half2 cnt[2] = {zero, zero};
+    __half2 cnt[2] = {zero, zero};  // !LDPC_PARITY_XOR: number of negative t per lane
+    unsigned par[2] = {0u, 0u};     // LDPC_PARITY_XOR: xor of the t patterns, bit 15 of a lane = sign parity
     __half2 sacc[2][SW];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -253,7 +268,10 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
                 const __half2 tt = __hsub2(t1, kbias);
                 const __half2 neg = neg01(tt);  // 1.0 where t < 0
                 sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
-                cnt[h] = __hadd2(cnt[h], neg);
+                if (LDPC_PARITY_XOR)
+                    par[h] ^= h2u(tt);
+                else
+                    cnt[h] = __hadd2(cnt[h], neg);
                 const __half2 key = __hfma2(__habs2(tt), eight, klh);
                 if (!EXACT) {
                     k2[h][s] = umin2(k2[h][s], umax2(k1[h][s], key));
@@ -278,7 +296,9 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
             }
         }
     }
-    unsigned nsg[2][SW];
+    unsigned nsg[2][SW], rwn[U4 * 4];
+#pragma unroll
+    for (int w = 6 + 2 * SW; w < U4 * 4; w++) rwn[w] = 0u;  // padding words of the record
     __half2 min1[2], idx[2], dnew[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -307,7 +327,8 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
         idx[h] = ix;
         dnew[h] = __hsub2(m2, m1);
         // parity of the negative-sign count -> 0xFFFF per lane; sign bits of all dc edges flip with it
-        const unsigned pm = (h2u(__hadd2(cnt[h], k1024)) & 0x00010001u) * 0xFFFFu;
+        const unsigned pm = LDPC_PARITY_XOR ? ((par[h] >> 15) & 0x00010001u) * 0xFFFFu
+                                            : (h2u(__hadd2(cnt[h], k1024)) & 0x00010001u) * 0xFFFFu;
 #pragma unroll
         for (int g = 0; g < SW; g++) {
             int gs = dc - g * kSignGroup;
@@ -315,13 +336,14 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
             const unsigned gm = ((1u << gs) - 1u) * 0x00010001u;
             nsg[h][g] = (h2u(__hadd2(sacc[h][g], k1024)) ^ pm) & gm;
         }
-        rw[h] = h2u(m1);
-        rw[2 + h] = h2u(m2);
-        rw[4 + h] = h2u(ix);
+        rwn[h] = h2u(m1);
+        rwn[2 + h] = h2u(m2);
+        rwn[4 + h] = h2u(ix);
 #pragma unroll
-        for (int g = 0; g < SW; g++) rw[6 + h * SW + g] = nsg[h][g];
+        for (int g = 0; g < SW; g++) rwn[6 + h * SW + g] = nsg[h][g];
     }
-    rec_store<U4>(recp, rw);
+    rec_store<U4>(recp, rwn);
+    if (LDPC_REC_PRELOAD && ld_next) rec_load<U4>(nx, rw);
 
 #pragma unroll
     for (int k = 0; k < DC; k++) {
@@ -342,23 +364,26 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
     }
 }
 
-// The record a thread needs in its NEXT step (its next row of this layer, else its first row of the next
-// layer / next iteration) is pulled into L1 one step ahead.  One step is ~2 us of lead (L2 or HBM latency is
-// covered) and only two steps of records (2 x T x 32..64 B) compete for the L1 space left beside the APP
-// words; prefetching a whole layer ahead (80 KB in flight for J15_L30_Z1280 against ~73 KB of L1) lost most
-// lines before their use (ncu: 26 % of the stall samples were long-scoreboard waits on the record load).
+// Address of the record a thread needs in its NEXT step (its next row of this layer, else its first row of
+// the next layer / next iteration) and whether that step reads a record at all; optional L1/L2 prefetch of
+// it (LDPC_REC_PREFETCH).  History: prefetching a whole layer ahead into L1 (80 KB in flight for
+// J15_L30_Z1280 against ~64 KB of L1) lost most lines before their use — ncu showed 26 % of the stall
+// samples as long-scoreboard waits on the record load; one step ahead was better, the register preload
+// (process_row_x) better still.
 template <int DCHI, bool FIRST>
-__device__ __forceinline__ void prefetch_next_record(const uint4 *recl, const uint4 *nxl, int i, int T, int Z,
-                                                     bool pf_next_layer)
+__device__ __forceinline__ bool prefetch_next_record(const uint4 *recl, const uint4 *nxl, int i, int T, int Z,
+                                                     bool pf_next_layer, const uint4 *&nx)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
-    if (!LDPC_REC_PREFETCH) return;
     const bool same_layer = i + T < Z;
-    const uint4 *nx = same_layer ? recl + (size_t)(i + T) * RS : nxl + (size_t)threadIdx.x * RS;
-    if (same_layer ? !FIRST : pf_next_layer) {
+    nx = same_layer ? recl + (size_t)(i + T) * RS : nxl + (size_t)threadIdx.x * RS;
+    const bool want = same_layer ? !FIRST : pf_next_layer;
+    if (LDPC_REC_PREFETCH == 1 && want) {
         prefetch_l1(nx);
         if (RecLayout<DCHI>::U4 > 2) prefetch_l1(nx + 2);
     }
+    if (LDPC_REC_PREFETCH == 2 && want) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+    return want;
 }
 
 // Rows of a layer whose degree is outside the exact range of the kernel's bucket.  Out of line so
@@ -371,16 +396,20 @@ __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p
     constexpr int RS = RecLayout<DCHI>::STRIDE;
     const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
     for (int i = threadIdx.x; i < Z; i += T) {
-        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer);
-        process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RS, amax8,
-                                                amax8p7, bmul, nbias);
+        const uint4 *nx;
+        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer, nx);
+        unsigned rw[RecLayout<DCHI>::U4 * 4];  // out of line: this path loads its record itself
+        if (!FIRST && LDPC_REC_PRELOAD) rec_load<RecLayout<DCHI>::U4>(recl + (size_t)i * RS, rw);
+        process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RS, nx, false,
+                                                rw, amax8, amax8p7, bmul, nbias);
     }
 }
 
 // One full iteration: all layers in order, the Z rows of a layer spread over the CTA.
 template <int DCHI, bool FIRST>
 __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec, bool last,
-                                             __half2 amax8, __half2 amax8p7, __half2 bmul, __half2 nbias)
+                                             unsigned (&rw)[RecLayout<DCHI>::U4 * 4], __half2 amax8,
+                                             __half2 amax8p7, __half2 bmul, __half2 nbias)
 {
     constexpr int RS = RecLayout<DCHI>::STRIDE;
     const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
@@ -393,9 +422,10 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         const bool pf_next_layer = (!FIRST || r == p.J - 1) && !(last && r == p.J - 1);
 #define LDPC_ROWS(DCX)                                                                                        \
     for (int i = tid; i < Z; i += T) {                                                                        \
-        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer);                                 \
-        process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * RS, amax8, \
-                                              amax8p7, bmul, nbias);                                          \
+        const uint4 *nx;                                                                                      \
+        const bool ldn = prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer, nx);            \
+        process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * RS, nx, ldn, \
+                                              rw, amax8, amax8p7, bmul, nbias);                               \
     }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
@@ -407,6 +437,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
             LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
             generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, nxl, pf_next_layer, amax8, amax8p7, bmul, nbias);
+            if (LDPC_REC_PRELOAD && pf_next_layer && tid < Z) rec_load<RecLayout<DCHI>::U4>(nxl + (size_t)tid * RS, rw);
         }
 #undef LDPC_ROWS
         __syncthreads();
@@ -632,12 +663,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 
         unsigned running = valid;  // frames not yet latched
         int it = 0;
+        unsigned rw[RecLayout<DCMAX>::U4 * 4];  // the record of the thread's next step (LDPC_REC_PRELOAD)
         while (it < p.iters) {
             it++;
             if (it == 1)
-                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amax8, amax8p7, bmul, nbias);
             else
-                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amax8, amax8p7, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 unsigned fail = 0u;
                 for (int r = 0; r < p.J; r++) {
