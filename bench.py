@@ -33,6 +33,9 @@ ITERS = 10
 EBN0_DB = 2.0
 # B_cw(it) = it*(2*E*w + 2*M*rec) + N*4 + N/8, int8: w = 1, rec = 4  -> 4 638 400 B at 10 it
 B_CW = ITERS * (2 * E * 1 + 2 * M * 4) + N * 4 + N // 8
+# dram__bytes_read.sum + dram__bytes_write.sum of one ldpc_layered_i8_kernel launch over 2368 frames, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_layered_i8_summary.txt (1.69 GB + 3.17 GB): per frame
+NCU_DRAM_BYTES_PER_FRAME = (1.693379e9 + 3.173281e9) / 2368
 METRIC = "decoded info Gbit/s at fixed iters"
 WORKLOAD = ("binary QC-LDPC J15_L30_Z1280 (N=38400, K=19200), BPSK-AWGN Eb/N0 2.0 dB, layered normalised "
             "min-sum (x0.875), int8 state, 10 iterations fixed, no early exit")
@@ -65,7 +68,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def __enter__(self):
         self.t.start()
@@ -203,19 +206,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the e2e region (nvidia-smi answers in
+    # ~50 ms, the device-timed region alone lasts ~0.2 s), all of it under decode load
+    clk = ClockSampler(local)
+    clk.__enter__()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     launches = 0
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clk:
-        barrier()
-        ev[0].record()
-        for i in range(args.steps):
-            launches += step()
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        barrier()
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        launches += step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)) / args.steps  # one launch per step
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -259,6 +265,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_fn_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
     del yh_fn
+    clk.__exit__()
 
     if rank == 0:
         peak, which = measured_peaks()
@@ -280,11 +287,18 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic, "peak_source": f"{which} (MEASURED_PEAKS.json, burst copy)",
+                         "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_FRAME * F,
+                         "traffic_source": "ncu --set full at F=2368 (profiles/r01_ncu_layered_i8_summary.txt), scaled "
+                                           "to this launch's frame count; mostly check records spilling from L2",
+                         "peak_source": f"{which} (MEASURED_PEAKS.json, burst copy)",
                          "kernel": "ldpc_layered_i8_kernel", "kernel_ms": kern_ms,
-                         "bytes_model": f"SURVEY 8(d): B_cw(10)={B_CW} B x {F} frames per launch; the design keeps "
-                                        "APP state in shared memory and check records in L2, so DRAM traffic is "
-                                        "I/O only (see DESIGN.md) and frac > 1 is possible"},
+                         "bytes_model": f"SURVEY 8(d): B_cw(10)={B_CW} B x {F} frames per launch (algorithmic bytes of a "
+                                        "streaming layered decoder).  This design keeps the APP state in shared "
+                                        "memory, so its real DRAM traffic is lower (traffic) and the pipe that binds is "
+                                        "the SM issue rate, not HBM: see issue_bound",
+                         "issue_bound": {"inst_per_edge_4frames": 57.5, "ipc_per_smsp": 0.66,
+                                         "practical_ipc_peak_per_smsp": 0.80,
+                                         "source": "profiles/r01_ncu_layered_i8_summary.txt, profiles/r01_pipe_ubench.txt"}},
         }
         try:
             line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_port()

@@ -23,8 +23,9 @@
 #include "philox.cuh"
 
 // Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it):
-//   LDPC_REC_PRELOAD   1  the record of a thread's next step is loaded into registers between the two phases
-//                         of the current row (9.07 -> 8.70 ms; an L1 or L2 prefetch on top of it LOSES 2 %)
+//   LDPC_REC_PRELOAD   2  the record of a thread's next step is loaded into registers right after the edge loop
+//                         of the current row (1 = after the record store): 9.07 -> 8.70 -> 8.45 ms; an L1 or L2
+//                         prefetch on top of it LOSES 2 %
 //   LDPC_REC_PREFETCH  0  1 = prefetch.global.L1, 2 = prefetch.global.L2 of the next step's record at row start
 //   LDPC_PARITY_XOR    1  sign parity as xor of the t patterns (LOP3) instead of an fp16 count (9.30 -> 9.06 ms)
 //   LDPC_LOAD_DEPTH    8  channel-value vectors in flight per thread in the load phase
@@ -39,7 +40,7 @@
 #define LDPC_PARITY_XOR 1
 #endif
 #ifndef LDPC_REC_PRELOAD
-#define LDPC_REC_PRELOAD 1
+#define LDPC_REC_PRELOAD 2
 #endif
 #ifndef LDPC_LOAD_DEPTH
 #define LDPC_LOAD_DEPTH 8
@@ -296,6 +297,9 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
             }
         }
     }
+    // the old record is dead: start the load of the next step's record, ~150 instructions of row finalisation
+    // and the whole phase 2 before its first use
+    if (LDPC_REC_PRELOAD == 2 && ld_next) rec_load<U4>(nx, rw);
     unsigned nsg[2][SW], rwn[U4 * 4];
 #pragma unroll
     for (int w = 6 + 2 * SW; w < U4 * 4; w++) rwn[w] = 0u;  // padding words of the record
@@ -343,7 +347,7 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
         for (int g = 0; g < SW; g++) rwn[6 + h * SW + g] = nsg[h][g];
     }
     rec_store<U4>(recp, rwn);
-    if (LDPC_REC_PRELOAD && ld_next) rec_load<U4>(nx, rw);
+    if (LDPC_REC_PRELOAD == 1 && ld_next) rec_load<U4>(nx, rw);
 
 #pragma unroll
     for (int k = 0; k < DC; k++) {

@@ -17,15 +17,18 @@
 
 namespace ldpcb {
 
-constexpr int kNbThreads = 256;
+constexpr int kNbThreads = 256;      // CTA width when the frame state lives in the global scratch slot
+constexpr int kNbThreadsMax = 1024;  // ... and the widest CTA tried when it fits in shared memory
 constexpr int kNmMax = 4;  // EMS_NM supported on the device path
 
 struct NbParams {
     const void *in;
     uint16_t *out;
     int *iters_out, *ok_out;
-    float *scratch;        // per CTA slot
+    float *scratch;        // per CTA slot (global memory), unused when slot_in_smem
     size_t slot_floats;
+    int slot_in_smem;      // the frame state sits in shared memory behind the algorithm's work arrays
+    size_t work_floats;    // size of those work arrays
     int F, N, M, q, p, dv_max, dc_max, n_const;
     int algo, in_kind, maxit, nm, nc;
     float sigma;
@@ -89,10 +92,22 @@ __device__ void syndrome(const NbParams &p, const uint16_t *sym, int *fail)
 struct EmsWarpShared {   // per warp, in shared memory
     float *E;             // [q]
     int *ie, *ih;         // [32] inputs of the task: edge slot in v2c/top, coefficient
+    int *cb, *hi;         // [32] h_j * best_j and h_j^-1
+    int *ds;              // [32][kNmMax] syndrome change when input j moves from its best to its k-th symbol
     float *tval;          // [32][kNmMax] best values of every input
     int *tsym;            // [32][kNmMax] and their symbols
 };
-__host__ __device__ constexpr size_t ems_warp_floats(int q) { return (size_t)q + 32 + 32 + 32 * kNmMax * 2; }
+__host__ __device__ constexpr size_t ems_warp_floats(int q) { return (size_t)q + 4 * 32 + 32 * kNmMax * 3; }
+
+// E[s] = max(E[s], v) on a float in shared memory (any signs, -inf included): non-negative floats order like
+// signed ints, negative floats like reversed unsigned ints
+__device__ __forceinline__ void atomic_max_float(float *addr, float v)
+{
+    if (v >= 0.0f)
+        atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
+}
 
 __device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const float *v2c, const uint16_t *topsym,
                                     const float *topval, float *c2v, const EmsWarpShared &ws, int lane)
@@ -101,18 +116,23 @@ __device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const fl
     if (lane < n) {  // inputs in ascending edge position, the output edge left out
         const int b = lane + (lane >= dc);
         const int e = p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b];
+        const int h = p.c_gf[row * p.dc_max + b];
         ws.ie[lane] = e;
-        ws.ih[lane] = p.c_gf[row * p.dc_max + b];
+        ws.ih[lane] = h;
+        const int cb = gmul(p, topsym[e * kNmMax], h);
+        ws.cb[lane] = cb;
+        ws.hi[lane] = __ldg(p.inv + h);
         for (int k = 0; k < p.nm; k++) {
             ws.tval[lane * kNmMax + k] = topval[e * kNmMax + k];
             ws.tsym[lane * kNmMax + k] = topsym[e * kNmMax + k];
+            ws.ds[lane * kNmMax + k] = cb ^ gmul(p, topsym[e * kNmMax + k], h);
         }
     }
     __syncwarp();
     int s0 = 0;
     float sum_top = 0.0f;
     for (int j = 0; j < n; j++) {
-        s0 ^= gmul(p, ws.tsym[j * kNmMax], ws.ih[j]);
+        s0 ^= ws.cb[j];
         sum_top = __fadd_rn(sum_top, ws.tval[j * kNmMax]);
     }
     const int Nc = (p.nc == p.dc_max - 1) ? w - 1 : p.nc;  // :297-304
@@ -123,7 +143,7 @@ __device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const fl
             const int best = ws.tsym[j * kNmMax], hj = ws.ih[j];
             const float *vj = v2c + (size_t)ws.ie[j] * q;
             if (hj != 0) {
-                const int a = gmul(p, __ldg(p.inv + hj), s ^ s0 ^ gmul(p, best, hj));
+                const int a = gmul(p, ws.hi[j], s ^ s0 ^ ws.cb[j]);
                 if (a != best) {
                     const float va = vj[a];
                     float sum = 0.0f;
@@ -142,31 +162,57 @@ __device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const fl
         ws.E[s] = e;
     }
     __syncwarp();
-    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1 — few leaves; every lane walks the same
-    // odometer (digits packed 2 bits per input in a register) and keeps the leaves on its own syndromes
-    unsigned long long ks = 0;
-    int diff = 0;
-    while (true) {
-        int s = 0;
-        float sum = 0.0f;
-        for (int j = 0; j < n; j++) {
-            const int k = (int)((ks >> (2 * j)) & 3ull);
-            s ^= gmul(p, ws.tsym[j * kNmMax + k], ws.ih[j]);
-            sum = __fadd_rn(sum, ws.tval[j * kNmMax + k]);
-        }
-        if ((s & 31) == lane && sum > ws.E[s]) ws.E[s] = sum;
-        int j = n - 1;
-        for (; j >= 0; j--) {  // increment digit j; reset and carry when it overflows or breaks the budget
-            const int k = (int)((ks >> (2 * j)) & 3ull);
-            if (k == 0) diff++;
-            if (k + 1 < p.nm && diff <= Nc) {
-                ks += 1ull << (2 * j);
-                break;
+    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1.  The all-best leaf and every single deviation are
+    // already in conf(q,1) above (same fresh sums), so for Nc <= 2 only the PAIRS of deviating inputs remain:
+    // C(n,2) (Nm-1)^2 leaves, dealt round-robin to the lanes; leaves of different lanes that land on the same
+    // syndrome meet in an atomic max (max is order-independent, the result stays exact).
+    if (Nc <= 2) {
+        const int nk = p.nm - 1, per_pair = nk * nk;
+        const int leaves = (Nc == 2) ? (n * (n - 1) / 2) * per_pair : 0;
+        for (int L = lane; L < leaves; L += 32) {
+            int P = L / per_pair;
+            const int kk = L - P * per_pair, k1 = 1 + kk / nk, k2 = 1 + kk - (kk / nk) * nk;
+            int j1 = 0;
+            for (int cnt = n - 1; P >= cnt; cnt--) {
+                P -= cnt;
+                j1++;
             }
-            ks &= ~(3ull << (2 * j));
-            diff--;
+            const int j2 = j1 + 1 + P;
+            const int sy = s0 ^ ws.ds[j1 * kNmMax + k1] ^ ws.ds[j2 * kNmMax + k2];
+            float sum = 0.0f;
+            for (int i = 0; i < n; i++)
+                sum = __fadd_rn(sum, ws.tval[i * kNmMax + ((i == j1) ? k1 : ((i == j2) ? k2 : 0))]);
+            atomic_max_float(ws.E + sy, sum);
         }
-        if (j < 0) break;
+    } else {  // general budget: every lane walks the same odometer (digits packed 2 bits per input) and
+              // evaluates every 32nd leaf
+        unsigned long long ks = 0;
+        int diff = 0, leaf = 0;
+        while (true) {
+            if ((leaf & 31) == lane) {
+                int sy = s0;
+                float sum = 0.0f;
+                for (int j = 0; j < n; j++) {
+                    const int k = (int)((ks >> (2 * j)) & 3ull);
+                    sy ^= ws.ds[j * kNmMax + k];
+                    sum = __fadd_rn(sum, ws.tval[j * kNmMax + k]);
+                }
+                atomic_max_float(ws.E + sy, sum);
+            }
+            leaf++;
+            int j = n - 1;
+            for (; j >= 0; j--) {  // increment digit j; reset and carry when it overflows or breaks the budget
+                const int k = (int)((ks >> (2 * j)) & 3ull);
+                if (k == 0) diff++;
+                if (k + 1 < p.nm && diff <= Nc) {
+                    ks += 1ull << (2 * j);
+                    break;
+                }
+                ks &= ~(3ull << (2 * j));
+                diff--;
+            }
+            if (j < 0) break;
+        }
     }
     __syncwarp();
     const int h = p.c_gf[row * p.dc_max + dc];
@@ -262,7 +308,10 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
                 ws.E = base;
                 ws.ie = reinterpret_cast<int *>(base + q);
                 ws.ih = ws.ie + 32;
-                ws.tval = base + q + 64;
+                ws.cb = ws.ih + 32;
+                ws.hi = ws.cb + 32;
+                ws.ds = ws.hi + 32;
+                ws.tval = base + q + 128 + 32 * kNmMax;
                 ws.tsym = reinterpret_cast<int *>(ws.tval + 32 * kNmMax);
                 ems_check_task_warp(p, row, dc, v2c, topsym, topval, c2v, ws, tid & 31);
             }
@@ -293,16 +342,16 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         s.vv[d * q + a] = __fsub_rn(LLR[vn * q + a], c2v[((size_t)row * p.dc_max + d) * q + a]);
     }
     __syncthreads();
-    if (a < w) {  // d_TMM_Get_Zn :704-723 (first minimum)
+    for (int d = a; d < w; d += q) {  // d_TMM_Get_Zn :704-723 (first minimum); dc may exceed q (GF(16), dc 21)
         float mn = INFINITY;
         int me = 0;
-        const int h = p.c_gf[row * p.dc_max + a];
+        const int h = p.c_gf[row * p.dc_max + d];
         for (int x = 0; x < q; x++)
-            if (s.vv[a * q + x] < mn) {
-                mn = s.vv[a * q + x];
+            if (s.vv[d * q + x] < mn) {
+                mn = s.vv[d * q + x];
                 me = gmul(p, x, h);
             }
-        s.Zn[a] = me;
+        s.Zn[d] = me;
     }
     __syncthreads();
     if (act && a == 0) {
@@ -586,20 +635,34 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
     }
 }
 
-__global__ void __launch_bounds__(kNbThreads)
+// Frame state (channel LLRs, a-posteriori vectors, both message arrays, EMS candidate lists): one slot per
+// CTA.  When the slot fits in shared memory beside the algorithm's work arrays it lives there (C4: 150 KB)
+// and the CTA is as wide as fits; otherwise (GF(256) EMS/FFT-BP: > 227 KB in fp32) it is a slice of the
+// handle's global scratch that stays L2-resident.  The decoders only see pointers.
+__host__ __device__ inline size_t nb_slot_floats(int algo, int N, int M, int q, int dv_max, int dc_max)
+{
+    size_t n = (size_t)N * (q - 1) + (size_t)N * q + (size_t)M * dc_max * q + (size_t)(N + 1) / 2 + 8;  // lch LLR c2v sym
+    if (algo == NB_ALGO_EMS || algo == NB_ALGO_FFT_BP) n += (size_t)N * dv_max * q;                      // v2c
+    if (algo == NB_ALGO_EMS) n += (size_t)N * dv_max * kNmMax + ((size_t)N * dv_max * kNmMax + 1) / 2;   // top lists
+    return (n + 63) & ~(size_t)63;
+}
+
+__global__ void __launch_bounds__(kNbThreadsMax)
 nb_decode_kernel(const __grid_constant__ NbParams p)
 {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_fail;
-    float *slot = p.scratch + (size_t)blockIdx.x * p.slot_floats;
+    float *slot = p.slot_in_smem ? smem + p.work_floats : p.scratch + (size_t)blockIdx.x * p.slot_floats;
     const int q = p.q, N = p.N, M = p.M;
+    const bool has_v2c = p.algo == NB_ALGO_EMS || p.algo == NB_ALGO_FFT_BP;
     float *lch = slot;
     float *LLR = lch + (size_t)N * (q - 1);
     float *c2v = LLR + (size_t)N * q;
     float *v2c = c2v + (size_t)M * p.dc_max * q;
-    float *topval = v2c + (size_t)N * p.dv_max * q;
-    uint16_t *topsym = reinterpret_cast<uint16_t *>(topval + (size_t)N * p.dv_max * kNmMax);
-    uint16_t *sym = topsym + (size_t)N * p.dv_max * kNmMax;
+    float *topval = v2c + (has_v2c ? (size_t)N * p.dv_max * q : 0);
+    const size_t ntop = p.algo == NB_ALGO_EMS ? (size_t)N * p.dv_max * kNmMax : 0;
+    uint16_t *topsym = reinterpret_cast<uint16_t *>(topval + ntop);
+    uint16_t *sym = topsym + ((ntop + 1) & ~(size_t)1);
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         demodulate(p, f, lch);
         __syncthreads();
@@ -682,34 +745,47 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
                             : (o->in_kind == NB_IN_BPSK)     ? (size_t)N * c->p
                                                              : (size_t)N * 2;
     const size_t in_bytes = in_elems * F * sizeof(float), out_bytes = (size_t)F * N * sizeof(uint16_t);
-    // shared memory: EMS check chunk (transposed E) or TMM group arrays
-    size_t smem = 0;
-    int ems_chunk = 0;
-    if (o->algo == NB_ALGO_EMS) {
-        ems_chunk = kNbThreads / 32;
-        smem = (size_t)ems_chunk * ems_warp_floats(q) * sizeof(float);  // E[q] + input lists per warp
-    } else if (o->algo == NB_ALGO_FFT_BP) {
-        if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;
+    if (o->algo == NB_ALGO_FFT_BP)
         for (int g : c->c_gf)
             if (g == 0) return LDPC_ERR_UNSUPPORTED;  // multiplication by 0 is not a permutation
-        smem = (size_t)(kNbThreads / q) * ((size_t)(c->dc_max + 2) * q + 4) * sizeof(float);
-    } else {
-        const int groups = (o->algo == NB_ALGO_LAYERED_TMM) ? 1 : (kNbThreads / q > 0 ? kNbThreads / q : 1);
-        if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA
-        smem = (size_t)groups * ((size_t)2 * c->dc_max * q + 7 * q + c->dc_max + 1) * sizeof(float);
-    }
+    if (o->algo != NB_ALGO_EMS && q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA
+    // shared-memory work arrays of a CTA of T threads: EMS E[q] + input lists per warp, FFT-BP / TMM group arrays
+    auto work_floats_of = [&](int T) -> size_t {
+        size_t w;
+        if (o->algo == NB_ALGO_EMS)
+            w = (size_t)(T / 32) * ems_warp_floats(q);
+        else if (o->algo == NB_ALGO_FFT_BP)
+            w = (size_t)(T / q) * ((size_t)(c->dc_max + 2) * q + 4);
+        else
+            w = (size_t)((o->algo == NB_ALGO_LAYERED_TMM) ? 1 : T / q) * ((size_t)2 * c->dc_max * q + 7 * q + c->dc_max + 1);
+        return (w + 3) & ~(size_t)3;
+    };
+    const size_t slot_floats = nb_slot_floats(o->algo, N, M, q, c->dv_max, c->dc_max);
+    // CTA shape (measured on B200, profiles/r01_nb_bench.txt): frames in flight per SM matter more than where the
+    // state lives, so EMS / TMM keep 256-thread CTAs (8 per SM) with the state in an L2-resident slot; the
+    // row-serial layered TMM runs one q-thread group per CTA (up to 32 CTAs per SM); FFT-BP, a chain of short
+    // barrier-separated stages, is fastest as one wide CTA with the whole frame state in shared memory.
+    int threads = kNbThreads, slot_in_smem = 0;
+    if (o->algo == NB_ALGO_LAYERED_TMM) threads = q < 64 ? 64 : ((q + 31) & ~31);
+    if (o->algo == NB_ALGO_FFT_BP)
+        for (int T = kNbThreadsMax; T >= kNbThreads; T >>= 1)
+            if ((work_floats_of(T) + slot_floats) * sizeof(float) <= (size_t)227 * 1024) {
+                threads = T;
+                slot_in_smem = 1;
+                break;
+            }
+    const size_t work_floats = work_floats_of(threads);
+    const size_t smem = (work_floats + (slot_in_smem ? slot_floats : 0)) * sizeof(float);
+    const int ems_chunk = threads / 32;
     if (smem > 227 * 1024) return LDPC_ERR_UNSUPPORTED;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(nb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nb_decode_kernel, kNbThreads, smem));
+    LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nb_decode_kernel, threads, smem));
     if (occ < 1) return LDPC_ERR_UNSUPPORTED;
     int grid = c->num_sms * occ;
     if (grid > F) grid = F;
-    size_t slot_floats = (size_t)N * (q - 1) + (size_t)N * q + (size_t)M * c->dc_max * q + (size_t)N * c->dv_max * q +
-                         (size_t)N * c->dv_max * kNmMax + ((size_t)N * c->dv_max * kNmMax + N) / 2 + 8;
-    slot_floats = (slot_floats + 63) & ~(size_t)63;
     const size_t a256 = 255;
-    size_t need = (size_t)grid * slot_floats * sizeof(float);
+    size_t need = slot_in_smem ? 256 : (size_t)grid * slot_floats * sizeof(float);
     const size_t o_in = need = (need + a256) & ~a256;
     need += host ? ((in_bytes + a256) & ~a256) : 0;
     const size_t o_out = need;
@@ -747,6 +823,8 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     }
     p.scratch = reinterpret_cast<float *>(base);
     p.slot_floats = slot_floats;
+    p.slot_in_smem = slot_in_smem;
+    p.work_floats = work_floats;
     p.F = F;
     p.N = N;
     p.M = M;
@@ -773,7 +851,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     p.c_pos = c->d_c_pos;
     p.cre = c->d_cre;
     p.cim = c->d_cim;
-    nb_decode_kernel<<<grid, kNbThreads, smem, st>>>(p);
+    nb_decode_kernel<<<grid, threads, smem, st>>>(p);
     LDPC_CUDA_TRY(cudaGetLastError());
     if (host) {
         LDPC_CUDA_TRY(cudaMemcpyAsync(hard_syms, base + o_out, out_bytes, cudaMemcpyDeviceToHost, st));

@@ -227,3 +227,63 @@ def test_fft_bp_vs_oracle(nb_oracle, gf_dir, meta, name, exp, snr, F):
     assert same[o_ok == 1].all()
     out_t, it_t, ok_t = code.decode(lch, 20, algo=m.ALGO_TMM)
     assert ok.sum() >= ok_t.sum() and ok.sum() >= F // 2
+
+
+@pytest.mark.parametrize("matrix,q,exp,snr,F", [("Tanner_74_9_Z128_GF16.txt", 16, 0, 5.5, 3),
+                                                 ("LDPC_N96_K48_GF256_d1_exp.txt", 256, 1, 4.0, 12)])
+def test_remaining_shipped_matrices(nb_oracle, gf_dir, matrix, q, exp, snr, F):
+    """The two NB files of the reference no BASELINE config names: the only large code
+    (N = 9472 symbols over GF(16), dc 20-21) and the short GF(256) one, BPSK, all three decoders."""
+    cfg = {"matrix": matrix, "q": q, "constellation": "Constellation/BPSK.txt", "n_qam": 2}
+    mt, gf, cs = paths(cfg, gf_dir)
+    h = orc_load(nb_oracle, cfg, gf_dir, exp)
+    code = m.NbLdpcCode(mt, None, cs, coef_is_exponent=bool(exp))
+    N, p = code.N, code.p
+    L = N * p
+    sym = np.zeros(N, np.int32)
+    tx = np.zeros(2 * L, np.float32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    sigma = nb_oracle.nb_orc_sigma(h, 0, snr)
+    seed = np.array([173, 173, 173], np.int32)
+    lch = np.zeros((F, N * (q - 1)), np.float32)
+    rx = np.zeros(2 * L, np.float32)
+    for f in range(F):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rx.ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rx.ctypes.data, lch[f].ctypes.data)
+    for a, summode in [(m.ALGO_EMS, 1), (m.ALGO_TMM, 0), (m.ALGO_LAYERED_TMM, 0)]:
+        o_out = np.zeros((F, N), np.int32); o_it = np.zeros(F, np.int32); o_ok = np.zeros(F, np.int32)
+        nb_oracle.nb_orc_decode_batch(h, a, summode, lch.ctypes.data, F, 8, 2, 2, o_out.ctypes.data,
+                                      o_it.ctypes.data, o_ok.ctypes.data)
+        out, it, ok = code.decode(lch, 8, algo=a)
+        assert (ok == o_ok).all() and (it == o_it).all(), (matrix, a)
+        assert (out.astype(np.int32) == o_out).all(), (matrix, a)
+
+
+@pytest.mark.parametrize("nm,nc", [(2, 1), (3, 2), (3, 3), (4, 2), (2, 3)])
+def test_ems_configuration_set_variants(nb_oracle, gf_dir, meta, nm, nc):
+    """conf(Nm,Nc) for other budgets than the reference's (2,2) default (NB/include/define.h:31-32):
+    pairs-only enumeration (Nc <= 2) and the general odometer (Nc = dc-1 = 3 here) against the oracle."""
+    cfg = meta["configs"]["BDS"]
+    mt, gf, cs = paths(cfg, gf_dir)
+    h = orc_load(nb_oracle, cfg, gf_dir, 0)
+    code = m.NbLdpcCode(mt, None, cs, coef_is_exponent=False)
+    N, q, p = code.N, code.q, code.p
+    F = 24
+    sym = np.zeros(N, np.int32)
+    L = N * p
+    tx = np.zeros(2 * L, np.float32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    sigma = nb_oracle.nb_orc_sigma(h, 0, 2.5)
+    seed = np.array([173, 173, 173], np.int32)
+    lch = np.zeros((F, N * (q - 1)), np.float32)
+    rx = np.zeros(2 * L, np.float32)
+    for f in range(F):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rx.ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rx.ctypes.data, lch[f].ctypes.data)
+    o_out = np.zeros((F, N), np.int32); o_it = np.zeros(F, np.int32); o_ok = np.zeros(F, np.int32)
+    nb_oracle.nb_orc_decode_batch(h, m.ALGO_EMS, 1, lch.ctypes.data, F, 20, nm, nc, o_out.ctypes.data,
+                                  o_it.ctypes.data, o_ok.ctypes.data)
+    out, it, ok = code.decode(lch, 20, algo=m.ALGO_EMS, ems_nm=nm, ems_nc=nc)
+    assert (ok == o_ok).all() and (it == o_it).all()
+    assert (out.astype(np.int32) == o_out).all()
+    assert o_ok.sum() > 0
