@@ -83,21 +83,28 @@ __device__ void syndrome(const NbParams &p, const uint16_t *sym, int *fail)
 }
 
 // ---- EMS, NB/src/LDPC_Decoder.cpp:172-359 -------------------------------------------------------
-// One (check, output edge) task per WARP: E[s] = max over conf(q,1) U conf(Nm,Nc) of the fresh sum
-// (inputs summed from 0.0f in ascending edge position, the oracle's `fresh` rule).  Lane l owns the
+// Warp-centric: a warp owns a variable node (lanes = symbols) in the node phase and a check row (lanes =
+// syndromes) in the check phase, so every access to the q-vectors of the frame state is one coalesced
+// warp-wide load/store and no thread ever loops serially over q.
+//
+// Check node: E_d[s] = max over conf(q,1) U conf(Nm,Nc) of the fresh sum (inputs summed from 0.0f in
+// ascending edge position, the oracle's `fresh` rule) for every output edge d of the row.  Lane l owns the
 // syndromes s = l, l+32, ...: for a fixed deviating input j the map a -> s is a bijection (h_j != 0), so
-// every lane finds "its" symbol a = h_j^-1 (s ^ s_rest) directly and no two lanes ever write the same
-// E[s] — no atomics, no serial enumeration of the q*(dc-1) single-deviation leaves by one thread.
-// E of the warp goes to shared memory only for the final permuted read-out.
+// every lane finds "its" symbol a = h_j^-1 (s ^ s_rest) directly and no two lanes write the same E[s].
+// The v2c vectors of the row's edges are staged in shared memory once per task.
 struct EmsWarpShared {   // per warp, in shared memory
     float *E;             // [q]
-    int *ie, *ih;         // [32] inputs of the task: edge slot in v2c/top, coefficient
-    int *cb, *hi;         // [32] h_j * best_j and h_j^-1
-    int *ds;              // [32][kNmMax] syndrome change when input j moves from its best to its k-th symbol
-    float *tval;          // [32][kNmMax] best values of every input
+    float *v;             // [dc_max][q] v2c vectors of the row's edges
+    int *ih;              // [32] coefficient of edge b
+    int *cb, *hi;         // [32] h_b * best_b and h_b^-1
+    int *ds;              // [32][kNmMax] syndrome change when edge b moves from its best to its k-th symbol
+    float *tval;          // [32][kNmMax] best values of every edge
     int *tsym;            // [32][kNmMax] and their symbols
 };
-__host__ __device__ constexpr size_t ems_warp_floats(int q) { return (size_t)q + 4 * 32 + 32 * kNmMax * 3; }
+__host__ __device__ constexpr size_t ems_warp_floats(int q, int dc_max)
+{
+    return (size_t)q + (size_t)dc_max * q + 3 * 32 + 32 * kNmMax * 3;
+}
 
 // E[s] = max(E[s], v) on a float in shared memory (any signs, -inf included): non-negative floats order like
 // signed ints, negative floats like reversed unsigned ints
@@ -109,17 +116,18 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v)
         atomicMin(reinterpret_cast<unsigned *>(addr), __float_as_uint(v));
 }
 
-__device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const float *v2c, const uint16_t *topsym,
-                                    const float *topval, float *c2v, const EmsWarpShared &ws, int lane)
+// output edges [d0, d1) of check `row`, one warp.  W = the row's degree as a compile-time constant (every loop
+// over edges unrolls, the output edge d becomes a constant and "i != d" disappears), 0 = any degree.
+template <int W>
+__device__ void ems_check_row_warp(const NbParams &p, int row, int d0, int d1, const float *v2c, const uint16_t *topsym,
+                                   const float *topval, float *c2v, const EmsWarpShared &ws, int lane)
 {
-    const int q = p.q, w = p.cw[row], n = w - 1;
-    if (lane < n) {  // inputs in ascending edge position, the output edge left out
-        const int b = lane + (lane >= dc);
-        const int e = p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b];
-        const int h = p.c_gf[row * p.dc_max + b];
-        ws.ie[lane] = e;
-        ws.ih[lane] = h;
+    const int q = p.q, w = W ? W : p.cw[row], n = w - 1;
+    if (lane < w) {
+        const int e = p.c_vn[row * p.dc_max + lane] * p.dv_max + p.c_pos[row * p.dc_max + lane];
+        const int h = p.c_gf[row * p.dc_max + lane];
         const int cb = gmul(p, topsym[e * kNmMax], h);
+        ws.ih[lane] = h;
         ws.cb[lane] = cb;
         ws.hi[lane] = __ldg(p.inv + h);
         for (int k = 0; k < p.nm; k++) {
@@ -128,192 +136,276 @@ __device__ void ems_check_task_warp(const NbParams &p, int row, int dc, const fl
             ws.ds[lane * kNmMax + k] = cb ^ gmul(p, topsym[e * kNmMax + k], h);
         }
     }
-    __syncwarp();
-    int s0 = 0;
-    float sum_top = 0.0f;
-    for (int j = 0; j < n; j++) {
-        s0 ^= ws.cb[j];
-        sum_top = __fadd_rn(sum_top, ws.tval[j * kNmMax]);
+    for (int b = 0; b < w; b++) {  // stage the v2c vectors (coalesced)
+        const float *src = v2c + ((size_t)p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b]) * q;
+        for (int a = lane; a < q; a += 32) ws.v[b * q + a] = src[a];
     }
+    __syncwarp();
+    int s_all = 0;
+#pragma unroll
+    for (int b = 0; b < w; b++) s_all ^= ws.cb[b];
     const int Nc = (p.nc == p.dc_max - 1) ? w - 1 : p.nc;  // :297-304
-    for (int s = lane; s < q; s += 32) {
-        float e = (s == s0) ? sum_top : -INFINITY;
-        // conf(q,1): input j at the symbol a that makes the syndrome s, everybody else at their best
-        for (int j = 0; j < n; j++) {
-            const int best = ws.tsym[j * kNmMax], hj = ws.ih[j];
-            const float *vj = v2c + (size_t)ws.ie[j] * q;
-            if (hj != 0) {
-                const int a = gmul(p, ws.hi[j], s ^ s0 ^ ws.cb[j]);
-                if (a != best) {
-                    const float va = vj[a];
+#pragma unroll
+    for (int d = W ? 0 : d0; d < (W ? W : d1); d++) {
+        if (W && (d < d0 || d >= d1)) continue;
+        // inputs = the other edges in ascending position
+        const int s0 = s_all ^ ws.cb[d];
+        float sum_top = 0.0f;
+#pragma unroll
+        for (int b = 0; b < w; b++)
+            if (b != d) sum_top = __fadd_rn(sum_top, ws.tval[b * kNmMax]);
+        for (int s = lane; s < q; s += 32) {
+            float e = (s == s0) ? sum_top : -INFINITY;
+            // conf(q,1): input j at the symbol a that makes the syndrome s, everybody else at their best.  a == best
+            // only happens for s == s0 and then reproduces sum_top exactly, so it needs no branch.
+#pragma unroll
+            for (int j = 0; j < w; j++) {
+                if (j == d) continue;
+                const int hj = ws.ih[j];
+                if (hj != 0) {
+                    const int a = gmul(p, ws.hi[j], s ^ s0 ^ ws.cb[j]);
+                    const float va = ws.v[j * q + a];
                     float sum = 0.0f;
-                    for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? va : ws.tval[i * kNmMax]);
+#pragma unroll
+                    for (int i = 0; i < w; i++)
+                        if (i != d) sum = __fadd_rn(sum, (i == j) ? va : ws.tval[i * kNmMax]);
                     e = fmaxf(e, sum);
-                }
-            } else if (s == s0) {  // coefficient 0 (raw *_exp files): every symbol of input j lands on s0
-                for (int a = 0; a < q; a++) {
-                    if (a == best) continue;
-                    float sum = 0.0f;
-                    for (int i = 0; i < n; i++) sum = __fadd_rn(sum, (i == j) ? vj[a] : ws.tval[i * kNmMax]);
-                    e = fmaxf(e, sum);
+                } else if (s == s0) {  // coefficient 0 (raw *_exp files): every symbol of input j lands on s0
+                    const int best = ws.tsym[j * kNmMax];
+                    for (int a = 0; a < q; a++) {
+                        if (a == best) continue;
+                        float sum = 0.0f;
+                        for (int i = 0; i < w; i++)
+                            if (i != d) sum = __fadd_rn(sum, (i == j) ? ws.v[j * q + a] : ws.tval[i * kNmMax]);
+                        e = fmaxf(e, sum);
+                    }
                 }
             }
+            ws.E[s] = e;
         }
-        ws.E[s] = e;
-    }
-    __syncwarp();
-    // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1.  The all-best leaf and every single deviation are
-    // already in conf(q,1) above (same fresh sums), so for Nc <= 2 only the PAIRS of deviating inputs remain:
-    // C(n,2) (Nm-1)^2 leaves, dealt round-robin to the lanes; leaves of different lanes that land on the same
-    // syndrome meet in an atomic max (max is order-independent, the result stays exact).
-    if (Nc <= 2) {
-        const int nk = p.nm - 1, per_pair = nk * nk;
-        const int leaves = (Nc == 2) ? (n * (n - 1) / 2) * per_pair : 0;
-        for (int L = lane; L < leaves; L += 32) {
-            int P = L / per_pair;
-            const int kk = L - P * per_pair, k1 = 1 + kk / nk, k2 = 1 + kk - (kk / nk) * nk;
-            int j1 = 0;
-            for (int cnt = n - 1; P >= cnt; cnt--) {
-                P -= cnt;
-                j1++;
-            }
-            const int j2 = j1 + 1 + P;
-            const int sy = s0 ^ ws.ds[j1 * kNmMax + k1] ^ ws.ds[j2 * kNmMax + k2];
-            float sum = 0.0f;
-            for (int i = 0; i < n; i++)
-                sum = __fadd_rn(sum, ws.tval[i * kNmMax + ((i == j1) ? k1 : ((i == j2) ? k2 : 0))]);
-            atomic_max_float(ws.E + sy, sum);
-        }
-    } else {  // general budget: every lane walks the same odometer (digits packed 2 bits per input) and
-              // evaluates every 32nd leaf
-        unsigned long long ks = 0;
-        int diff = 0, leaf = 0;
-        while (true) {
-            if ((leaf & 31) == lane) {
-                int sy = s0;
+        __syncwarp();
+        // conf(Nm,Nc): at most Nc inputs at sorted index 1..Nm-1.  The all-best leaf and every single deviation
+        // are already in conf(q,1) (same fresh sums), so for Nc <= 2 only the PAIRS of deviating inputs remain:
+        // C(n,2) (Nm-1)^2 leaves, dealt round-robin to the lanes; leaves of different lanes that land on the
+        // same syndrome meet in an atomic max (max is order-independent, the result stays exact).
+        if (Nc <= 2) {
+            const int nk = p.nm - 1, per_pair = nk * nk;
+            const int leaves = (Nc == 2) ? (n * (n - 1) / 2) * per_pair : 0;
+            for (int L = lane; L < leaves; L += 32) {
+                int P = L / per_pair;
+                const int kk = L - P * per_pair, k1 = 1 + kk / nk, k2 = 1 + kk - (kk / nk) * nk;
+                int j1 = 0;
+                for (int cnt = n - 1; P >= cnt; cnt--) {
+                    P -= cnt;
+                    j1++;
+                }
+                int j2 = j1 + 1 + P;
+                j1 += (j1 >= d);  // input index -> edge position
+                j2 += (j2 >= d);
+                const int sy = s0 ^ ws.ds[j1 * kNmMax + k1] ^ ws.ds[j2 * kNmMax + k2];
                 float sum = 0.0f;
-                for (int j = 0; j < n; j++) {
-                    const int k = (int)((ks >> (2 * j)) & 3ull);
-                    sy ^= ws.ds[j * kNmMax + k];
-                    sum = __fadd_rn(sum, ws.tval[j * kNmMax + k]);
-                }
+#pragma unroll
+                for (int i = 0; i < w; i++)
+                    if (i != d) sum = __fadd_rn(sum, ws.tval[i * kNmMax + ((i == j1) ? k1 : ((i == j2) ? k2 : 0))]);
                 atomic_max_float(ws.E + sy, sum);
             }
-            leaf++;
-            int j = n - 1;
-            for (; j >= 0; j--) {  // increment digit j; reset and carry when it overflows or breaks the budget
-                const int k = (int)((ks >> (2 * j)) & 3ull);
-                if (k == 0) diff++;
-                if (k + 1 < p.nm && diff <= Nc) {
-                    ks += 1ull << (2 * j);
-                    break;
+        } else {  // general budget: every lane walks the same odometer (digits packed 2 bits per input) and
+                  // evaluates every 32nd leaf
+            unsigned long long ks = 0;
+            int diff = 0, leaf = 0;
+            while (true) {
+                if ((leaf & 31) == lane) {
+                    int sy = s0;
+                    float sum = 0.0f;
+                    for (int j = 0; j < n; j++) {
+                        const int k = (int)((ks >> (2 * j)) & 3ull), bj = j + (j >= d);
+                        sy ^= ws.ds[bj * kNmMax + k];
+                        sum = __fadd_rn(sum, ws.tval[bj * kNmMax + k]);
+                    }
+                    atomic_max_float(ws.E + sy, sum);
                 }
-                ks &= ~(3ull << (2 * j));
-                diff--;
+                leaf++;
+                int j = n - 1;
+                for (; j >= 0; j--) {  // increment digit j; reset and carry when it overflows or breaks the budget
+                    const int k = (int)((ks >> (2 * j)) & 3ull);
+                    if (k == 0) diff++;
+                    if (k + 1 < p.nm && diff <= Nc) {
+                        ks += 1ull << (2 * j);
+                        break;
+                    }
+                    ks &= ~(3ull << (2 * j));
+                    diff--;
+                }
+                if (j < 0) break;
             }
-            if (j < 0) break;
+        }
+        __syncwarp();
+        const int h = ws.ih[d];
+        float *m = c2v + ((size_t)row * p.dc_max + d) * q;
+        const float e0 = ws.E[0];
+        for (int k = 1 + lane; k < q; k += 32) {
+            const float df = __fsub_rn(ws.E[gmul(p, k, h)], e0);
+            m[k - 1] = (float)((double)df / 1.2);  // float difference, double division (:309)
+        }
+        __syncwarp();
+    }
+}
+
+// (value, list position) order of the stable descending sort of [1, 2, ..., q-1, 0] (BubleSort :17-36)
+__device__ __forceinline__ bool ems_before(float xa, int ia, float xb, int ib) { return xa > xb || (xa == xb && ia < ib); }
+
+// Variable node `col`, one warp: LLR = L_ch + sum_d c2v_d, decision (DecideLLRVector :71-91), and — the frame
+// not having converged is only known after the syndrome, so this work is wasted once per frame — v2c = LLR - c2v
+// per edge with the first Nm entries of its sorted list.
+// PER = symbols per lane (q <= 32 PER), DV = the node's degree as a constant (0 = any)
+template <int PER, int DV>
+__device__ void ems_var_node_warp(const NbParams &p, int col, const float *lch, const float *c2v, float *v2c,
+                                  float *topval, uint16_t *topsym, uint16_t *sym, int lane)
+{
+    constexpr int kMaxPerLane = PER, per = PER;
+    const int q = p.q, dv = DV ? DV : p.vw[col];
+    float llr[kMaxPerLane];  // symbol a = lane + 32 t (a = 0: the implicit 0)
+    const float *mv[kMaxDv];
+#pragma unroll
+    for (int d = 0; d < dv; d++)
+        mv[d] = c2v + ((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q;
+    float mx = 0.0f;
+    int best = 0;
+#pragma unroll
+    for (int t = 0; t < kMaxPerLane; t++) {
+        const int a = lane + 32 * t;
+        if (t < per && a >= 1 && a < q) {
+            float v = lch[col * (q - 1) + a - 1];
+#pragma unroll
+            for (int d = 0; d < dv; d++) v = __fadd_rn(v, mv[d][a - 1]);
+            llr[t] = v;
+            if (v > mx) {  // ascending a within the lane: the first maximum stays
+                mx = v;
+                best = a;
+            }
+        } else {
+            llr[t] = 0.0f;
         }
     }
-    __syncwarp();
-    const int h = p.c_gf[row * p.dc_max + dc];
-    float *m = c2v + ((size_t)row * p.dc_max + dc) * q;
-    const float e0 = ws.E[0];
-    for (int k = 1 + lane; k < q; k += 32) {
-        const float d = __fsub_rn(ws.E[gmul(p, k, h)], e0);
-        m[k - 1] = (float)((double)d / 1.2);  // float difference, double division (:309)
+    // warp argmax, lowest symbol on ties (the serial scan keeps the first strict maximum)
+    for (int o = 16; o > 0; o >>= 1) {
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if (omx > mx || (omx == mx && ob < best)) {
+            mx = omx;
+            best = ob;
+        }
     }
-    __syncwarp();
+    if (lane == 0) sym[col] = (uint16_t)((mx <= 0.0f) ? 0 : best);
+#pragma unroll
+    for (int d = 0; d < dv; d++) {
+        const int e = col * p.dv_max + d;
+        float x[kMaxPerLane];
+        bool used[kMaxPerLane];
+#pragma unroll
+        for (int t = 0; t < kMaxPerLane; t++) {
+            const int a = lane + 32 * t;
+            used[t] = !(t < per && a < q);
+            x[t] = (t < per && a >= 1 && a < q) ? __fsub_rn(llr[t], mv[d][a - 1]) : 0.0f;
+            if (!used[t]) v2c[(size_t)e * q + a] = x[t];
+        }
+        for (int k = 0; k < p.nm; k++) {
+            float bx = -INFINITY;
+            int bi = 0x7fffffff, bt = -1;  // list position i: a-1 for a >= 1, q-1 for a = 0
+#pragma unroll
+            for (int t = 0; t < kMaxPerLane; t++) {
+                const int a = lane + 32 * t, i = (a == 0) ? q - 1 : a - 1;
+                if (!used[t] && (bt < 0 || ems_before(x[t], i, bx, bi))) {
+                    bx = x[t];
+                    bi = i;
+                    bt = t;
+                }
+            }
+            float wx = bx;
+            int wi = bi;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ox = __shfl_xor_sync(0xffffffffu, wx, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                if (oi != 0x7fffffff && (wi == 0x7fffffff || ems_before(ox, oi, wx, wi))) {
+                    wx = ox;
+                    wi = oi;
+                }
+            }
+            if (bt >= 0 && bi == wi) {  // this lane holds the winner: retire it and publish
+#pragma unroll
+                for (int t = 0; t < kMaxPerLane; t++)
+                    if (t == bt) used[t] = true;
+                topval[e * kNmMax + k] = wx;
+                topsym[e * kNmMax + k] = (uint16_t)((wi == q - 1) ? 0 : wi + 1);
+            }
+        }
+    }
 }
 
 __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, float *c2v, float *v2c, float *topval,
                            uint16_t *topsym, uint16_t *sym, float *smemE, int *s_fail)
 {
     const int q = p.q, N = p.N, M = p.M, tid = threadIdx.x, T = blockDim.x;
+    const int warp = tid >> 5, nwarps = T >> 5, lane = tid & 31;
     for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 0.0f;
+    if (tid == 0) *s_fail = 0;
     __syncthreads();
+    // output edges of a row are split over several warps when there are fewer rows than 2 x warps (C5: M = 12)
+    int split = (2 * nwarps + M - 1) / M;
+    split = split < 1 ? 1 : (split > p.dc_max ? p.dc_max : split);
     int it = 0, ok = 0;
     while (it < p.maxit) {
         it++;
-        // variable nodes: LLR = L_ch + sum_d c2v_d, decide (DecideLLRVector :71-91)
-        for (int i = tid; i < N * (q - 1); i += T) {
-            const int col = i / (q - 1), a = i - col * (q - 1);
-            float v = lch[i];
-            for (int d = 0; d < p.vw[col]; d++)
-                v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + a]);
-            LLR[col * q + a] = v;
-        }
-        if (tid == 0) *s_fail = 0;
-        __syncthreads();
-        for (int col = tid; col < N; col += T) {
-            float mx = 0.0f;
-            int best = 0;
-            for (int a = 0; a < q - 1; a++)
-                if (LLR[col * q + a] > mx) {
-                    mx = LLR[col * q + a];
-                    best = a + 1;
-                }
-            sym[col] = (uint16_t)((mx <= 0.0f) ? 0 : best);
+        for (int col = warp; col < N; col += nwarps) {
+            const int dv = p.vw[col];
+#define VN(PER)                                                                                                \
+    if (dv == 2)                                                                                               \
+        ems_var_node_warp<PER, 2>(p, col, lch, c2v, v2c, topval, topsym, sym, lane);                           \
+    else if (dv == 3)                                                                                          \
+        ems_var_node_warp<PER, 3>(p, col, lch, c2v, v2c, topval, topsym, sym, lane);                           \
+    else                                                                                                       \
+        ems_var_node_warp<PER, 0>(p, col, lch, c2v, v2c, topval, topsym, sym, lane);
+            if (q <= 32) {
+                VN(1)
+            } else if (q <= 64) {
+                VN(2)
+            } else if (q <= 128) {
+                VN(4)
+            } else {
+                VN(8)
+            }
+#undef VN
         }
         __syncthreads();
         syndrome(p, sym, s_fail);
         __syncthreads();
-        if (*s_fail == 0) {
+        const int fail = *s_fail;
+        __syncthreads();
+        if (tid == 0) *s_fail = 0;
+        if (fail == 0) {
             ok = 1;
             it--;  // the reference returns iterations-1 on success (:236)
             break;
         }
-        // v2c = LLR - c2v by symbol (symbol 0 = 0), and the first Nm entries of the stable descending
-        // sort of the list [1, 2, ..., q-1, 0] (BubleSort :17-36)
-        for (int e = tid; e < N * p.dv_max; e += T) {
-            const int col = e / p.dv_max, d = e - col * p.dv_max;
-            if (d >= p.vw[col]) continue;
-            const float *m = c2v + ((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q;
-            float *v = v2c + (size_t)e * q;
-            float tv[kNmMax];
-            int ts[kNmMax];
-            for (int k = 0; k < kNmMax; k++) {
-                tv[k] = -INFINITY;
-                ts[k] = -1;
-            }
-            for (int i = 0; i < q; i++) {
-                const int a = (i < q - 1) ? i + 1 : 0;
-                const float x = (a == 0) ? 0.0f : __fsub_rn(LLR[col * q + a - 1], m[a - 1]);
-                v[a] = x;
-                // insert behind every entry that is >= x (ties keep list order)
-                int pos = p.nm;
-                for (int k = p.nm - 1; k >= 0; k--)
-                    if (ts[k] < 0 || x > tv[k]) pos = k;
-                for (int k = p.nm - 1; k > pos; k--) {
-                    tv[k] = tv[k - 1];
-                    ts[k] = ts[k - 1];
-                }
-                if (pos < p.nm) {
-                    tv[pos] = x;
-                    ts[pos] = a;
-                }
-            }
-            for (int k = 0; k < p.nm; k++) {
-                topval[e * kNmMax + k] = tv[k];
-                topsym[e * kNmMax + k] = (uint16_t)ts[k];
-            }
-        }
-        __syncthreads();
-        // check nodes: one (check, output edge) task per warp, E[q] of the warp in shared memory
-        const int tasks = M * p.dc_max, warp = tid >> 5, nwarps = T >> 5;
-        for (int t = warp; t < tasks; t += nwarps) {
-            const int row = t / p.dc_max, dc = t - row * p.dc_max;
-            if (dc < p.cw[row]) {
-                float *base = smemE + (size_t)warp * ems_warp_floats(q);
-                EmsWarpShared ws;
-                ws.E = base;
-                ws.ie = reinterpret_cast<int *>(base + q);
-                ws.ih = ws.ie + 32;
-                ws.cb = ws.ih + 32;
-                ws.hi = ws.cb + 32;
-                ws.ds = ws.hi + 32;
-                ws.tval = base + q + 128 + 32 * kNmMax;
-                ws.tsym = reinterpret_cast<int *>(ws.tval + 32 * kNmMax);
-                ems_check_task_warp(p, row, dc, v2c, topsym, topval, c2v, ws, tid & 31);
+        float *base = smemE + (size_t)warp * ems_warp_floats(q, p.dc_max);
+        EmsWarpShared ws;
+        ws.E = base;
+        ws.v = base + q;
+        ws.ih = reinterpret_cast<int *>(ws.v + (size_t)p.dc_max * q);
+        ws.cb = ws.ih + 32;
+        ws.hi = ws.cb + 32;
+        ws.ds = ws.hi + 32;
+        ws.tval = reinterpret_cast<float *>(ws.ds + 32 * kNmMax);
+        ws.tsym = reinterpret_cast<int *>(ws.tval + 32 * kNmMax);
+        for (int t = warp; t < M * split; t += nwarps) {
+            const int row = t / split, u = t - row * split, w = p.cw[row];
+            const int d0 = (u * w) / split, d1 = ((u + 1) * w) / split;
+            if (d0 >= d1) continue;
+            switch (w) {
+#define X(W) case W: ems_check_row_warp<W>(p, row, d0, d1, v2c, topsym, topval, c2v, ws, lane); break;
+                X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#undef X
+                default: ems_check_row_warp<0>(p, row, d0, d1, v2c, topsym, topval, c2v, ws, lane);
             }
         }
         __syncthreads();
@@ -748,12 +840,12 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     if (o->algo == NB_ALGO_FFT_BP)
         for (int g : c->c_gf)
             if (g == 0) return LDPC_ERR_UNSUPPORTED;  // multiplication by 0 is not a permutation
-    if (o->algo != NB_ALGO_EMS && q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA
+    if (q > kNbThreads) return LDPC_ERR_UNSUPPORTED;  // q = 512 needs a wider CTA (no shipped code uses GF(512))
     // shared-memory work arrays of a CTA of T threads: EMS E[q] + input lists per warp, FFT-BP / TMM group arrays
     auto work_floats_of = [&](int T) -> size_t {
         size_t w;
         if (o->algo == NB_ALGO_EMS)
-            w = (size_t)(T / 32) * ems_warp_floats(q);
+            w = (size_t)(T / 32) * ems_warp_floats(q, c->dc_max);
         else if (o->algo == NB_ALGO_FFT_BP)
             w = (size_t)(T / q) * ((size_t)(c->dc_max + 2) * q + 4);
         else
