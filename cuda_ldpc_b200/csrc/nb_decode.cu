@@ -598,11 +598,13 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
 
 
 // ---- FFT-BP (not in the reference; rules = oracle/nb_oracle.c decode_fftbp) ------------------------
-// Check node in the Walsh-Hadamard domain: GF(2^p) addition is XOR, so the convolution of the
-// (permuted) input distributions is a pointwise product of their WHTs.  q threads per check; the
-// butterflies run in shared memory in the oracle's pairing.  A dense [dc x q] x H_q contraction on the
-// tensor cores is the alternative the north star mentions; at q <= 256 and dc <= 12 the transform is
-// 8 butterfly stages on 12 KB and is not the bottleneck of this path.
+// Check node in the Walsh-Hadamard domain: GF(2^p) addition is XOR, so the convolution of the (permuted)
+// input distributions is a pointwise product of their WHTs.  q threads per check; ALL output edges of the
+// row go through the inverse transform and the normalising sum together (one barrier per butterfly / tree
+// stage for the whole row instead of one per stage and output edge).  Sums are pairwise trees
+// (t[x] += t[x + len], len = q/2 ... 1 — the oracle's tree_sum) so that they parallelise without changing a
+// bit.  A dense [dc x q] x H_q contraction on the tensor cores is the alternative the north star mentions; at
+// q <= 256 and dc <= 12 the transform is 8 butterfly stages on 12 KB and is not the bottleneck of this path.
 __device__ __forceinline__ void wht_stage_all(float *F, int q, int w, int a)
 {
     for (int len = 1; len < q; len <<= 1) {
@@ -618,68 +620,144 @@ __device__ __forceinline__ void wht_stage_all(float *F, int q, int w, int a)
     }
 }
 
+// tree sum of q values spread over a warp (element a = lane + 32 t), result in every lane
+template <int PER>
+__device__ __forceinline__ float warp_tree_sum(float (&x)[PER], int q)
+{
+#pragma unroll
+    for (int lt = PER / 2; lt >= 1; lt >>= 1)
+#pragma unroll
+        for (int t = 0; t < lt; t++) x[t] = __fadd_rn(x[t], x[t + lt]);
+    float v = x[0];
+    for (int len = (q < 32 ? q : 32) / 2; len >= 1; len >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, len));
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// variable node `col`, one warp: decision on pch * prod_d c2v_d, then v2c_d = normalised pch * prod_{d2 != d} c2v_d2
+template <int PER>
+__device__ void fft_var_node_warp(const NbParams &p, int col, const float *pch, const float *c2v, float *v2c,
+                                  uint16_t *sym, int lane)
+{
+    const int q = p.q, dv = p.vw[col];
+    float pc[PER];
+    float best = -1.0f;
+    int bi = 0;
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+        const int a = lane + 32 * t;
+        pc[t] = (a < q) ? pch[col * q + a] : 0.0f;
+        if (a < q) {
+            float v = pc[t];
+            for (int d = 0; d < dv; d++)
+                v = __fmul_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + a]);
+            if (v > best) {
+                best = v;
+                bi = a;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {  // first maximum = lowest symbol on ties
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    if (lane == 0) sym[col] = (uint16_t)bi;
+    for (int d = 0; d < dv; d++) {
+        float x[PER], xs[PER];
+#pragma unroll
+        for (int t = 0; t < PER; t++) {
+            const int a = lane + 32 * t;
+            float v = pc[t];
+            if (a < q)
+                for (int d2 = 0; d2 < dv; d2++)
+                    if (d2 != d)
+                        v = __fmul_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d2] * p.dc_max + p.v_pos[col * p.dv_max + d2]) * q + a]);
+            x[t] = xs[t] = v;
+        }
+        const float sum = warp_tree_sum<PER>(xs, q);
+#pragma unroll
+        for (int t = 0; t < PER; t++) {
+            const int a = lane + 32 * t;
+            if (a < q) v2c[((size_t)col * p.dv_max + d) * q + a] = __fdiv_rn(x[t], sum);
+        }
+    }
+}
+
+// channel probabilities: pch = normalised exp(L - max(0, max L)), one warp per column
+template <int PER>
+__device__ void fft_init_warp(const NbParams &p, int col, const float *lch, float *pch, int lane)
+{
+    const int q = p.q;
+    float l[PER], e[PER], es[PER];
+    float mx = 0.0f;
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+        const int a = lane + 32 * t;
+        l[t] = (a >= 1 && a < q) ? lch[col * (q - 1) + a - 1] : 0.0f;
+        mx = fmaxf(mx, l[t]);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+        const int a = lane + 32 * t;
+        e[t] = es[t] = (a < q) ? expf(__fsub_rn(l[t], mx)) : 0.0f;
+    }
+    const float sum = warp_tree_sum<PER>(es, q);
+#pragma unroll
+    for (int t = 0; t < PER; t++) {
+        const int a = lane + 32 * t;
+        if (a < q) pch[col * q + a] = __fdiv_rn(e[t], sum);
+    }
+}
+
 __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, float *c2v, float *v2c, uint16_t *sym,
                              float *smem, int *s_fail)
 {
     const int q = p.q, N = p.N, M = p.M, tid = threadIdx.x, T = blockDim.x;
-    for (int col = tid; col < N; col += T) {
-        float mx = 0.0f;
-        for (int a = 0; a < q - 1; a++) mx = fmaxf(mx, lch[col * (q - 1) + a]);
-        float s = 0.0f;
-        for (int a = 0; a < q; a++) {
-            const float v = expf(__fsub_rn(a ? lch[col * (q - 1) + a - 1] : 0.0f, mx));
-            pch[col * q + a] = v;
-            s = __fadd_rn(s, v);
-        }
-        for (int a = 0; a < q; a++) pch[col * q + a] = __fdiv_rn(pch[col * q + a], s);
+    const int warp = tid >> 5, nwarps = T >> 5, lane = tid & 31;
+#define FFT_PER(CALL)          \
+    if (q <= 32) {             \
+        CALL(1)                \
+    } else if (q <= 64) {      \
+        CALL(2)                \
+    } else if (q <= 128) {     \
+        CALL(4)                \
+    } else {                   \
+        CALL(8)                \
+    }
+    for (int col = warp; col < N; col += nwarps) {
+#define CALL(PER) fft_init_warp<PER>(p, col, lch, pch, lane);
+        FFT_PER(CALL)
+#undef CALL
     }
     for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 1.0f;
+    if (tid == 0) *s_fail = 0;
     __syncthreads();
     const int groups = max(1, T / q), g = tid / q, a = tid - g * q;
-    const size_t per_group = (size_t)(p.dc_max + 2) * q + 4;
-    float *F = smem + (size_t)(g < groups ? g : 0) * per_group, *G = F + p.dc_max * q, *tmp = G + q, *ssum = tmp + q;
+    const size_t per_group = (size_t)2 * p.dc_max * q;
+    float *F = smem + (size_t)(g < groups ? g : 0) * per_group, *G = F + (size_t)p.dc_max * q;
     int it = 0, ok = 0;
     while (it < p.maxit) {
         it++;
-        if (tid == 0) *s_fail = 0;
-        for (int col = tid; col < N; col += T) {
-            float best = -1.0f;
-            int bi = 0;
-            for (int x = 0; x < q; x++) {
-                float v = pch[col * q + x];
-                for (int d = 0; d < p.vw[col]; d++)
-                    v = __fmul_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
-                if (v > best) {
-                    best = v;
-                    bi = x;
-                }
-            }
-            sym[col] = (uint16_t)bi;
+        for (int col = warp; col < N; col += nwarps) {
+#define CALL(PER) fft_var_node_warp<PER>(p, col, pch, c2v, v2c, sym, lane);
+            FFT_PER(CALL)
+#undef CALL
         }
         __syncthreads();
         syndrome(p, sym, s_fail);
         __syncthreads();
-        if (*s_fail == 0) {
+        const int fail = *s_fail;
+        __syncthreads();
+        if (tid == 0) *s_fail = 0;
+        if (fail == 0) {
             ok = 1;
             it--;
             break;
         }
-        for (int e = tid; e < N * p.dv_max; e += T) {
-            const int col = e / p.dv_max, d = e - col * p.dv_max;
-            if (d >= p.vw[col]) continue;
-            float *v = v2c + (size_t)e * q;
-            float s = 0.0f;
-            for (int x = 0; x < q; x++) {
-                float t = pch[col * q + x];
-                for (int d2 = 0; d2 < p.vw[col]; d2++)
-                    if (d2 != d)
-                        t = __fmul_rn(t, c2v[((size_t)p.v_cn[col * p.dv_max + d2] * p.dc_max + p.v_pos[col * p.dv_max + d2]) * q + x]);
-                v[x] = t;
-                s = __fadd_rn(s, t);
-            }
-            for (int x = 0; x < q; x++) v[x] = __fdiv_rn(v[x], s);
-        }
-        __syncthreads();
         const int rounds = (M + groups - 1) / groups;
         for (int r = 0; r < rounds; r++) {
             const int row = r * groups + g;
@@ -691,36 +769,35 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
             }
             __syncthreads();
             wht_stage_all(F, q, w, a);
-            for (int d = 0; d < p.dc_max; d++) {  // same trip count for every group: barriers stay aligned
-                const bool on = d < w;
-                if (on) {
-                    float gy = 1.0f;
-                    bool first = true;
-                    for (int d2 = 0; d2 < w; d2++) {
-                        if (d2 == d) continue;
-                        gy = first ? F[d2 * q + a] : __fmul_rn(gy, F[d2 * q + a]);
-                        first = false;
-                    }
-                    G[a] = gy;
+            for (int d = 0; d < w; d++) {  // products of the other edges' transforms, ascending edge position
+                float gy = 1.0f;
+                bool first = true;
+                for (int d2 = 0; d2 < w; d2++) {
+                    if (d2 == d) continue;
+                    gy = first ? F[d2 * q + a] : __fmul_rn(gy, F[d2 * q + a]);
+                    first = false;
                 }
-                __syncthreads();
-                wht_stage_all(G, q, on ? 1 : 0, a);
-                if (on) {
-                    const float gv = G[gmul(p, a, p.c_gf[row * p.dc_max + d])];
-                    tmp[a] = gv > 1e-30f ? gv : 1e-30f;
-                }
-                __syncthreads();
-                if (on && a == 0) {
-                    float s = 0.0f;
-                    for (int x = 0; x < q; x++) s = __fadd_rn(s, tmp[x]);
-                    ssum[0] = s;
-                }
-                __syncthreads();
-                if (on) c2v[((size_t)row * p.dc_max + d) * q + a] = __fdiv_rn(tmp[a], ssum[0]);
+                G[d * q + a] = gy;
+            }
+            __syncthreads();
+            wht_stage_all(G, q, w, a);
+            for (int d = 0; d < w; d++) {  // permute back, clamp; F is dead and takes the clamped values
+                const float gv = G[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])];
+                F[d * q + a] = gv > 1e-30f ? gv : 1e-30f;
+            }
+            __syncthreads();
+            for (int d = 0; d < w; d++) G[d * q + a] = F[d * q + a];
+            __syncthreads();
+            for (int len = q / 2; len >= 1; len >>= 1) {  // tree sums of all output edges
+                if (a < len)
+                    for (int d = 0; d < w; d++) G[d * q + a] = __fadd_rn(G[d * q + a], G[d * q + a + len]);
                 __syncthreads();
             }
+            for (int d = 0; d < w; d++) c2v[((size_t)row * p.dc_max + d) * q + a] = __fdiv_rn(F[d * q + a], G[d * q]);
+            __syncthreads();
         }
     }
+#undef FFT_PER
     if (tid == 0) {
         if (p.iters_out) p.iters_out[f] = it;
         if (p.ok_out) p.ok_out[f] = ok;
@@ -847,7 +924,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
         if (o->algo == NB_ALGO_EMS)
             w = (size_t)(T / 32) * ems_warp_floats(q, c->dc_max);
         else if (o->algo == NB_ALGO_FFT_BP)
-            w = (size_t)(T / q) * ((size_t)(c->dc_max + 2) * q + 4);
+            w = (size_t)(T / q) * ((size_t)2 * c->dc_max * q);
         else
             w = (size_t)((o->algo == NB_ALGO_LAYERED_TMM) ? 1 : T / q) * ((size_t)2 * c->dc_max * q + 7 * q + c->dc_max + 1);
         return (w + 3) & ~(size_t)3;

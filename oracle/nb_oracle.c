@@ -645,10 +645,20 @@ static void wht(float *v, int q)
             }
 }
 
+/* Sums of the FFT-BP decoder are pairwise trees, t[x] += t[x + len] for len = q/2 ... 1 (q is a power of
+ * two): the order a GPU reduction follows, so that the kernel can be compared bit for bit. */
+static float tree_sum(const float *v, int q)
+{
+    float t[512];
+    for (int a = 0; a < q; a++) t[a] = v[a];
+    for (int len = q / 2; len >= 1; len >>= 1)
+        for (int x = 0; x < len; x++) t[x] = t[x] + t[x + len];
+    return t[0];
+}
+
 static void normalise(float *v, int q)
 {
-    float s = 0.0f;
-    for (int a = 0; a < q; a++) s = s + v[a];
+    const float s = tree_sum(v, q);
     for (int a = 0; a < q; a++) v[a] = v[a] / s;
 }
 
