@@ -419,6 +419,7 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
 // ---- TMM / layered TMM, NB/src/LDPC_Decoder.cpp:361-817 -----------------------------------------
 struct TmmShared {
     float *vv, *dU, *Min1, *Min2, *I, *Ev;  // per group: [dc_max*q], [dc_max*q], [q] x4
+    int2 *MC;                               // [q] {Min1 bits, MinCol}
     int *MinCol, *Path, *Zn;                // [q], [2q], [dc_max + 1] (last = syndrome)
 };
 
@@ -434,16 +435,40 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         s.vv[d * q + a] = __fsub_rn(LLR[vn * q + a], c2v[((size_t)row * p.dc_max + d) * q + a]);
     }
     __syncthreads();
-    for (int d = a; d < w; d += q) {  // d_TMM_Get_Zn :704-723 (first minimum); dc may exceed q (GF(16), dc 21)
-        float mn = INFINITY;
-        int me = 0;
-        const int h = p.c_gf[row * p.dc_max + d];
-        for (int x = 0; x < q; x++)
-            if (s.vv[d * q + x] < mn) {
-                mn = s.vv[d * q + x];
-                me = gmul(p, x, h);
+    // d_TMM_Get_Zn :704-723: hard symbol of every edge = first minimum of its v2c vector.  q >= 32: one warp of
+    // the group per edge (lanes scan x = lane, lane+32, ... then a warp argmin, lowest x on ties); dc may exceed q
+    if (q >= 32) {
+        const int lane = a & 31;
+        for (int d = a >> 5; d < w; d += q >> 5) {
+            float mn = INFINITY;
+            int mx = 0;
+            for (int x = lane; x < q; x += 32)
+                if (s.vv[d * q + x] < mn) {
+                    mn = s.vv[d * q + x];
+                    mx = x;
+                }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float on = __shfl_xor_sync(0xffffffffu, mn, o);
+                const int ox = __shfl_xor_sync(0xffffffffu, mx, o);
+                if (on < mn || (on == mn && ox < mx)) {
+                    mn = on;
+                    mx = ox;
+                }
             }
-        s.Zn[d] = me;
+            if (lane == 0) s.Zn[d] = gmul(p, mx, p.c_gf[row * p.dc_max + d]);
+        }
+    } else {
+        for (int d = a; d < w; d += q) {
+            float mn = INFINITY;
+            int me = 0;
+            const int h = p.c_gf[row * p.dc_max + d];
+            for (int x = 0; x < q; x++)
+                if (s.vv[d * q + x] < mn) {
+                    mn = s.vv[d * q + x];
+                    me = gmul(p, x, h);
+                }
+            s.Zn[d] = me;
+        }
     }
     __syncthreads();
     if (act && a == 0) {
@@ -472,34 +497,32 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         s.Min1[a] = m1;
         s.Min2[a] = m2;
         s.MinCol[a] = col;
+        s.MC[a] = make_int2(__float_as_int(m1), col);
     }
     __syncthreads();
-    if (act) {  // TMM_ConstructConf :772-817
+    if (act) {  // TMM_ConstructConf :772-817.  dU[MinCol[j]][j] IS Min1[j], so the two-deviation search reads one
+                // {Min1, MinCol} pair per symbol (a broadcast for j, a permutation for a ^ j) and selects without branches:
+                // "(d1 > d2 && d1 < I) or (d1 < d2 && d2 < I)"  ==  "d1 != d2 && max(d1, d2) < I"
         float Ii = 0.0f, Ei = 0.0f;
         int p0 = -1, p1 = -1;
         if (a != 0) {
-            Ii = s.dU[s.MinCol[a] * q + a];
+            const float m1a = s.Min1[a];
+            Ii = m1a;
             p0 = p1 = s.MinCol[a];
-            Ei = s.Min2[a];
+            bool two = false;
+#pragma unroll 4
             for (int j = 0; j < q; j++) {
-                if (j == a) continue;
-                const int k = a ^ j;
-                const int cj = s.MinCol[j], ck = s.MinCol[k];
-                if (cj != ck) {
-                    const float d1 = s.dU[cj * q + j], d2 = s.dU[ck * q + k];
-                    if (d1 > d2 && d1 < Ii) {
-                        Ii = d1;
-                        p0 = cj;
-                        p1 = ck;
-                        Ei = s.Min1[a];
-                    } else if (d1 < d2 && d2 < Ii) {
-                        Ii = d2;
-                        p0 = cj;
-                        p1 = ck;
-                        Ei = s.Min1[a];
-                    }
+                const int2 ej = s.MC[j], ek = s.MC[a ^ j];
+                const float d1 = __int_as_float(ej.x), d2 = __int_as_float(ek.x);
+                const float m = fmaxf(d1, d2);
+                if (j != a && ej.y != ek.y && d1 != d2 && m < Ii) {
+                    Ii = m;
+                    p0 = ej.y;
+                    p1 = ek.y;
+                    two = true;
                 }
             }
+            Ei = two ? m1a : s.Min2[a];
         }
         s.I[a] = Ii;
         s.Ev[a] = Ei;
@@ -538,13 +561,14 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
     // thread groups of q threads: one check per group (layered: a single group keeps the row order)
     const int groups = layered ? 1 : max(1, T / q);
     const int g = tid / q, a = tid - g * q;
-    const size_t per_group = (size_t)2 * p.dc_max * q + 4 * q + q + 2 * q + p.dc_max + 1;
+    const size_t per_group = ((size_t)2 * p.dc_max * q + 9 * q + p.dc_max + 1 + 3) & ~(size_t)3;
     TmmShared s;
     {
         float *base = smem + (size_t)(g < groups ? g : 0) * per_group;
         s.vv = base;
         s.dU = s.vv + p.dc_max * q;
-        s.Min1 = s.dU + p.dc_max * q;
+        s.MC = reinterpret_cast<int2 *>(s.dU + p.dc_max * q);
+        s.Min1 = s.dU + p.dc_max * q + 2 * q;
         s.Min2 = s.Min1 + q;
         s.I = s.Min2 + q;
         s.Ev = s.I + q;
@@ -926,7 +950,8 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
         else if (o->algo == NB_ALGO_FFT_BP)
             w = (size_t)(T / q) * ((size_t)2 * c->dc_max * q);
         else
-            w = (size_t)((o->algo == NB_ALGO_LAYERED_TMM) ? 1 : T / q) * ((size_t)2 * c->dc_max * q + 7 * q + c->dc_max + 1);
+            w = (size_t)((o->algo == NB_ALGO_LAYERED_TMM) ? 1 : T / q) *
+                (((size_t)2 * c->dc_max * q + 9 * q + c->dc_max + 1 + 3) & ~(size_t)3);
         return (w + 3) & ~(size_t)3;
     };
     const size_t slot_floats = nb_slot_floats(o->algo, N, M, q, c->dv_max, c->dc_max);
