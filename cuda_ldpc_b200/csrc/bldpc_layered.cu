@@ -675,15 +675,23 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             else
                 sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amax8, amax8p7, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
-                unsigned fail = 0u;
+                // The pass stops after the first layer that leaves every running frame with a failed check (the
+                // usual case until the last iterations: one layer of J is read instead of all) — the outcome
+                // "not converged" is then already exact for all of them.
+                unsigned rbytes = 0u;  // 0x80 in the byte of every running frame
+#pragma unroll
+                for (int j = 0; j < 4; j++) rbytes |= ((running >> j) & 1u) ? (0x80u << (8 * j)) : 0u;
+                unsigned fl = 0u;
                 for (int r = 0; r < p.J; r++) {
                     const int dc = p.lt.dc[r], off = p.lt.off[r];
+                    unsigned fail = 0u;
                     for (int i = tid; i < Z; i += T) fail |= syndrome_row(smem, p, off, dc, 4 * i, Z4);
+                    fail = __reduce_or_sync(0xffffffffu, fail);
+                    if ((tid & 31) == 0 && fail) atomicOr(&s_fail, fail);
+                    __syncthreads();
+                    fl = s_fail;
+                    if ((fl & rbytes) == rbytes) break;  // uniform: every thread reads the same word
                 }
-                fail = __reduce_or_sync(0xffffffffu, fail);
-                if ((tid & 31) == 0 && fail) atomicOr(&s_fail, fail);
-                __syncthreads();
-                const unsigned fl = s_fail;
                 __syncthreads();
                 if (tid == 0) s_fail = 0u;
                 // okmask bit j = frame j satisfies all checks
