@@ -33,6 +33,7 @@ struct NbParams {
     int algo, in_kind, maxit, nm, nc;
     float sigma;
     int ems_chunk;         // EMS check tasks per shared-memory chunk
+    int ems_full;          // log-QSPA (NB/src/Simulation.cpp:64-67): every configuration, Nm = q, Nc = dc - 1
     const uint16_t *mul, *inv;
     const int *vw, *cw, *v_cn, *v_pos, *c_vn, *c_gf, *c_pos;
     const float *cre, *cim;
@@ -251,6 +252,63 @@ __device__ void ems_check_row_warp(const NbParams &p, int row, int d0, int d1, c
     }
 }
 
+// log-QSPA, the reference's decoder_method 2 = Decoding_EMS(..., GFQ, maxdc - 1, ...) (NB/src/Simulation.cpp:64-67):
+// every one of the q^(dc-1) configurations.  The fresh sum of a configuration is a left-to-right sum over the
+// inputs, and floating-point addition is monotone in its first argument, so the maximum over all
+// configurations with syndrome s equals — bit for bit — the forward (max,+) recursion
+//   F_0[s] = (s == 0 ? 0.0f : -inf),   F_j[s] = max_t ( F_{j-1}[s ^ t] + v_j[h_j^-1 t] ),
+// O(dc q^2) per output edge instead of q^(dc-1).  One warp per row slice; lane l owns the syndromes l, l+32, ...
+// (s ^ t keeps the lanes on distinct banks); the permuted vectors v_j[h_j^-1 t] are staged once per row.
+__device__ void ems_check_row_full_warp(const NbParams &p, int row, int d0, int d1, const float *v2c, float *c2v,
+                                        const EmsWarpShared &ws, int lane)
+{
+    const int q = p.q, w = p.cw[row];
+    float *Fa = ws.E, *Fb = reinterpret_cast<float *>(ws.ds);  // 3 * 32 * kNmMax >= q words
+    if (lane < w) ws.ih[lane] = p.c_gf[row * p.dc_max + lane];
+    __syncwarp();
+    for (int b = 0; b < w; b++) {
+        const float *src = v2c + ((size_t)p.c_vn[row * p.dc_max + b] * p.dv_max + p.c_pos[row * p.dc_max + b]) * q;
+        const int h = ws.ih[b];
+        if (h != 0) {
+            const int hinv = __ldg(p.inv + h);
+            for (int t = lane; t < q; t += 32) ws.v[b * q + t] = src[gmul(p, hinv, t)];
+        } else {  // coefficient 0 (raw *_exp files): every symbol contributes syndrome 0
+            float mx = -INFINITY;
+            for (int a = lane; a < q; a += 32) mx = fmaxf(mx, src[a]);
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (int t = lane; t < q; t += 32) ws.v[b * q + t] = (t == 0) ? mx : -INFINITY;
+        }
+    }
+    __syncwarp();
+    for (int d = d0; d < d1; d++) {
+        float *F = Fa, *Fn = Fb;
+        for (int s = lane; s < q; s += 32) F[s] = (s == 0) ? 0.0f : -INFINITY;
+        __syncwarp();
+        for (int j = 0; j < w; j++) {
+            if (j == d) continue;
+            const float *vp = ws.v + j * q;
+            for (int s = lane; s < q; s += 32) {
+                float e = -INFINITY;
+#pragma unroll 4
+                for (int t = 0; t < q; t++) e = fmaxf(e, __fadd_rn(F[s ^ t], vp[t]));
+                Fn[s] = e;
+            }
+            __syncwarp();
+            float *tmp = F;
+            F = Fn;
+            Fn = tmp;
+        }
+        const int h = ws.ih[d];
+        float *m = c2v + ((size_t)row * p.dc_max + d) * q;
+        const float e0 = F[0];
+        for (int k = 1 + lane; k < q; k += 32) {
+            const float df = __fsub_rn(F[gmul(p, k, h)], e0);
+            m[k - 1] = (float)((double)df / 1.2);  // float difference, double division (:309)
+        }
+        __syncwarp();
+    }
+}
+
 // (value, list position) order of the stable descending sort of [1, 2, ..., q-1, 0] (BubleSort :17-36)
 __device__ __forceinline__ bool ems_before(float xa, int ia, float xb, int ib) { return xa > xb || (xa == xb && ia < ib); }
 
@@ -401,6 +459,10 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
             const int row = t / split, u = t - row * split, w = p.cw[row];
             const int d0 = (u * w) / split, d1 = ((u + 1) * w) / split;
             if (d0 >= d1) continue;
+            if (p.ems_full) {
+                ems_check_row_full_warp(p, row, d0, d1, v2c, c2v, ws, lane);
+                continue;
+            }
             switch (w) {
 #define X(W) case W: ems_check_row_warp<W>(p, row, d0, d1, v2c, topsym, topval, c2v, ws, lane); break;
                 X(2) X(3) X(4) X(5) X(6) X(7) X(8)
@@ -921,7 +983,11 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
         return LDPC_ERR_ARG;
     if (o->in_kind < 0 || o->in_kind > 2) return LDPC_ERR_ARG;
     nb_ldpc_code *c = const_cast<nb_ldpc_code *>(cc);
-    if (o->algo == NB_ALGO_EMS && (o->ems_nm < 1 || o->ems_nm > kNmMax || o->ems_nc < 0)) return LDPC_ERR_UNSUPPORTED;
+    // EMS budgets: Nm <= 4 sorted entries per input with any Nc, or the reference's log-QSPA setting
+    // (decoder_method 2: Nm = q, Nc = dc_max - 1 = every configuration)
+    const bool ems_full = o->algo == NB_ALGO_EMS && o->ems_nm >= c->q && o->ems_nc >= c->dc_max - 1;
+    if (o->algo == NB_ALGO_EMS && !ems_full && (o->ems_nm < 1 || o->ems_nm > kNmMax || o->ems_nc < 0))
+        return LDPC_ERR_UNSUPPORTED;
     if (o->in_kind == NB_IN_BPSK && c->n_const != 2) return LDPC_ERR_ARG;
     if (o->in_kind == NB_IN_QAM && c->n_const != c->q) return LDPC_ERR_ARG;
     if (o->in_kind != NB_IN_SYMBOL_LLR && !(o->sigma > 0.0f)) return LDPC_ERR_ARG;
@@ -1030,7 +1096,8 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     p.algo = o->algo;
     p.in_kind = o->in_kind;
     p.maxit = iters;
-    p.nm = o->ems_nm;
+    p.nm = ems_full ? 0 : o->ems_nm;
+    p.ems_full = ems_full ? 1 : 0;
     p.nc = o->ems_nc;
     p.sigma = o->sigma;
     p.ems_chunk = ems_chunk;

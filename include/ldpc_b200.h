@@ -202,7 +202,8 @@ typedef struct {
     int algo;        /* NB_ALGO_* */
     int in_kind;     /* NB_IN_*   */
     int mem_space;   /* LDPC_MEM_* */
-    int ems_nm;      /* EMS_NM (NB/include/define.h:31) */
+    int ems_nm;      /* EMS_NM (NB/include/define.h:31): 1..4 sorted entries per input, or q with ems_nc = dc_max-1 =
+                        the reference's log-QSPA setting, decoder_method 2 (NB/src/Simulation.cpp:64-67) */
     int ems_nc;      /* EMS_NC (:32) */
     float sigma;     /* for the fused demappers */
     int *iters_out;  /* [F] iter_number as the reference returns it (iterations-1 on success) */

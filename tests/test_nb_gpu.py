@@ -287,3 +287,42 @@ def test_ems_configuration_set_variants(nb_oracle, gf_dir, meta, nm, nc):
     assert (ok == o_ok).all() and (it == o_it).all()
     assert (out.astype(np.int32) == o_out).all()
     assert o_ok.sum() > 0
+
+
+def test_log_qspa_full_configuration_set(nb_oracle, gf_dir, meta):
+    """decoder_method 2 of the reference = Decoding_EMS(..., GFQ, maxdc - 1, ...) (NB/src/Simulation.cpp:64-67):
+    every one of the q^(dc-1) configurations.  The kernel's (max,+) forward recursion must reproduce the
+    oracle's explicit enumeration bit for bit (3 iterations of 2 frames: the enumeration is 5e7 leaves per
+    frame and iteration)."""
+    cfg = meta["configs"]["BDS"]
+    mt, gf, cs = paths(cfg, gf_dir)
+    h = orc_load(nb_oracle, cfg, gf_dir, 0)
+    code = m.NbLdpcCode(mt, None, cs, coef_is_exponent=False)
+    N, q, p = code.N, code.q, code.p
+    F, L = 2, N * p
+    sym = np.zeros(N, np.int32)
+    tx = np.zeros(2 * L, np.float32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    sigma = nb_oracle.nb_orc_sigma(h, 0, 1.5)
+    seed = np.array([173, 173, 173], np.int32)
+    lch = np.zeros((F, N * (q - 1)), np.float32)
+    rx = np.zeros(2 * L, np.float32)
+    for f in range(F):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rx.ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rx.ctypes.data, lch[f].ctypes.data)
+    dc_max = 4
+    o_out = np.zeros((F, N), np.int32); o_it = np.zeros(F, np.int32); o_ok = np.zeros(F, np.int32)
+    nb_oracle.nb_orc_decode_batch(h, m.ALGO_EMS, 1, lch.ctypes.data, F, 3, q, dc_max - 1, o_out.ctypes.data,
+                                  o_it.ctypes.data, o_ok.ctypes.data)
+    out, it, ok = code.decode(lch, 3, algo=m.ALGO_EMS, ems_nm=q, ems_nc=dc_max - 1)
+    assert (ok == o_ok).all() and (it == o_it).all()
+    assert (out.astype(np.int32) == o_out).all()
+    # and it decodes: at a comfortable SNR the full set converges at least as often as EMS(2,2)
+    sigma2 = nb_oracle.nb_orc_sigma(h, 0, 2.5)
+    rxs = np.zeros((32, L), np.float32)
+    for f in range(32):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma2, tx.ctypes.data, rx.ctypes.data, L)
+        rxs[f] = rx[0::2]
+    _, _, ok_full = code.decode(rxs, 20, algo=m.ALGO_EMS, in_kind=m.IN_BPSK, sigma=sigma2, ems_nm=q, ems_nc=dc_max - 1)
+    _, _, ok_22 = code.decode(rxs, 20, algo=m.ALGO_EMS, in_kind=m.IN_BPSK, sigma=sigma2)
+    assert ok_full.sum() >= ok_22.sum() - 1 and ok_full.sum() >= 16
