@@ -28,7 +28,7 @@ struct Args {
 
 static void usage()
 {
-    printf("usage: nb_ldpc_sim --matrix FILE --constellation FILE [--gf FILE] [--exp] [--algo ems|tmm|ltmm|fftbp]\n"
+    printf("usage: nb_ldpc_sim --matrix FILE --constellation FILE [--gf FILE] [--exp] [--algo ems|tmm|ltmm|fftbp|logqspa]\n"
            "       [--nm n --nc n] [--snr a b step] [--snrtype 0|1] [--maxit n] [--batch F] [--least-errors n]\n"
            "       [--least-frames n] [--max-frames n] [--gpus g] [--seed s] [--codeword FILE]\n");
 }
@@ -54,7 +54,11 @@ int main(int argc, char **argv)
         else if (s == "--constellation") a.constellation = next(), i++;
         else if (s == "--codeword") a.codeword = next(), i++;
         else if (s == "--exp") a.exp = 1;
-        else if (s == "--algo") { std::string m = next(); i++; a.algo = m == "tmm" ? NB_ALGO_TMM : m == "ltmm" ? NB_ALGO_LAYERED_TMM : m == "fftbp" ? NB_ALGO_FFT_BP : NB_ALGO_EMS; }
+        else if (s == "--algo") {
+            std::string m = next(); i++;
+            a.algo = m == "tmm" ? NB_ALGO_TMM : m == "ltmm" ? NB_ALGO_LAYERED_TMM : m == "fftbp" ? NB_ALGO_FFT_BP : NB_ALGO_EMS;
+            if (m == "logqspa") a.nm = a.nc = 1 << 20;  // decoder_method 2: Nm = q, Nc = dc-1 (clamped by the library's test >=)
+        }
         else if (s == "--nm") a.nm = atoi(next()), i++;
         else if (s == "--nc") a.nc = atoi(next()), i++;
         else if (s == "--snr") a.snr_start = atof(next(1)), a.snr_stop = atof(next(2)), a.snr_step = atof(next(3)), i += 3;
