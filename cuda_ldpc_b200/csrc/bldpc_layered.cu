@@ -2,8 +2,7 @@
 //
 // B200 mapping:
 //  * one CTA decodes a GROUP of 4 codewords at a time; their APP values live in shared memory
-//    for the whole decode as one 32-bit word per code bit (4 x biased uint8), so HBM sees
-//    only the channel values in and the hard decisions out;
+//    for the whole decode as one 32-bit word per code bit (4 x biased uint8);
 //  * thread = check row i of the current layer (block row of H); the circulant shift is the
 //    shared-memory address (i + s) mod Z, consecutive threads hit consecutive banks;
 //  * arithmetic is 2-way SIMD on half2 lanes holding small integers (exact in fp16 below 2048):
@@ -11,7 +10,10 @@
 //    (VIMNMX.U16x2, VIMNMX3.U16x2, VIADDMNMX.S16x2.RELU) — sm_100a has no native 8x4 SIMD integer
 //    min/compare (the __v*4 intrinsics expand to 5-10 instructions, profiles/r01_simd_sass.txt);
 //  * the compressed check record {min1, min2, idx, sign bits} is streamed through a per-CTA
-//    slice of a scratch buffer that stays L2-resident (148 CTAs x M x 32 B << 126 MB);
+//    slice of a scratch buffer (L2 evict-last; for J15_L30_Z1280 the 148 x 19200 x 32 B = 91 MB do
+//    not stay in L2 beside the streaming input, about half of the record reads come from HBM —
+//    ~2 MB of DRAM traffic per frame, a quarter of the HBM peak); each thread loads the record of
+//    its NEXT row into registers while it finishes the current one, which hides that latency;
 //  * the syndrome (early exit / ok flag) is a cheap extra pass: XOR of the sign bits.
 //
 // Update rules: exactly oracle/bldpc_oracle.c "int8 layered rules" (t = APP - c2v_old,
@@ -77,7 +79,7 @@ struct LayeredParams {
 };
 
 // Check records: 256-bit global accesses with the L2 evict-last policy (LDG.E.ELL2.256 /
-// STG.E.ELL2.256 on sm_100a) so that the per-CTA record slices stay L2-resident while the
+// STG.E.ELL2.256 on sm_100a) so that the per-CTA record slices are the last thing L2 gives up while the
 // channel values stream through; the trailing 128 bits of wide records use a plain access.
 template <int U4>
 __device__ __forceinline__ void rec_load(const uint4 *p, unsigned *rw)

@@ -39,7 +39,22 @@ struct NbParams {
     const float *cre, *cim;
 };
 
-__device__ __forceinline__ int gmul(const NbParams &p, int a, int b) { return __ldg(p.mul + a * p.q + b); }
+// GF(q) multiply table.  Default: the read-only path (LDG.CONSTANT; 8 KB for GF(64), 128 KB for GF(256) stay
+// L1/L2-resident).  NB_MUL_SMEM=1 keeps a copy in shared memory for q <= 64 (what BASELINE.json's north star
+// asks for) — measured on B200 it is SLOWER (C4 EMS 16.2 -> 17.4 ms, TMM 7.5 -> 7.7, layered TMM 4.1 -> 4.6 ms per
+// 8192 frames): L1 and shared memory are the same SRAM, the LDS saves nothing over an L1 hit, and 8 KB per CTA
+// costs the q-thread layered CTAs their 32-per-SM occupancy.
+#ifndef NB_MUL_SMEM
+#define NB_MUL_SMEM 0
+#endif
+constexpr int kMulSmemQ = 64;
+__shared__ uint16_t g_smul[NB_MUL_SMEM ? kMulSmemQ * kMulSmemQ : 1];
+constexpr size_t kNbDynSmemMax = (size_t)227 * 1024 - (NB_MUL_SMEM ? sizeof(uint16_t) * kMulSmemQ * kMulSmemQ : 0) - 64;  // minus the static part
+__device__ __forceinline__ int gmul(const NbParams &p, int a, int b)
+{
+    if (NB_MUL_SMEM && p.q <= kMulSmemQ) return g_smul[a * p.q + b];
+    return __ldg(p.mul + a * p.q + b);
+}
 
 // ---- Demodulate, NB/src/LDPC_Decoder.cpp:132-171 -------------------------------------------------
 __device__ void demodulate(const NbParams &p, int f, float *lch)
@@ -909,6 +924,10 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
     __shared__ int s_fail;
     float *slot = p.slot_in_smem ? smem + p.work_floats : p.scratch + (size_t)blockIdx.x * p.slot_floats;
     const int q = p.q, N = p.N, M = p.M;
+    if (NB_MUL_SMEM && q <= kMulSmemQ) {
+        for (int i = threadIdx.x; i < q * q; i += blockDim.x) g_smul[i] = p.mul[i];
+        __syncthreads();
+    }
     const bool has_v2c = p.algo == NB_ALGO_EMS || p.algo == NB_ALGO_FFT_BP;
     float *lch = slot;
     float *LLR = lch + (size_t)N * (q - 1);
@@ -1022,14 +1041,14 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     };
     const size_t slot_floats = nb_slot_floats(o->algo, N, M, q, c->dv_max, c->dc_max);
     // CTA shape (measured on B200, profiles/r01_nb_bench.txt): frames in flight per SM matter more than where the
-    // state lives, so EMS / TMM keep 256-thread CTAs (8 per SM) with the state in an L2-resident slot; the
+    // state lives, so EMS / TMM keep 256-thread CTAs (4-8 per SM) with the state in a global-scratch slot (L2); the
     // row-serial layered TMM runs one q-thread group per CTA (up to 32 CTAs per SM); FFT-BP, a chain of short
     // barrier-separated stages, is fastest as one wide CTA with the whole frame state in shared memory.
     int threads = kNbThreads, slot_in_smem = 0;
     if (o->algo == NB_ALGO_LAYERED_TMM) threads = q < 64 ? 64 : ((q + 31) & ~31);
     if (o->algo == NB_ALGO_FFT_BP)
         for (int T = kNbThreadsMax; T >= kNbThreads; T >>= 1)
-            if ((work_floats_of(T) + slot_floats) * sizeof(float) <= (size_t)227 * 1024) {
+            if ((work_floats_of(T) + slot_floats) * sizeof(float) <= kNbDynSmemMax) {
                 threads = T;
                 slot_in_smem = 1;
                 break;
@@ -1037,7 +1056,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     const size_t work_floats = work_floats_of(threads);
     const size_t smem = (work_floats + (slot_in_smem ? slot_floats : 0)) * sizeof(float);
     const int ems_chunk = threads / 32;
-    if (smem > 227 * 1024) return LDPC_ERR_UNSUPPORTED;
+    if (smem > kNbDynSmemMax) return LDPC_ERR_UNSUPPORTED;
     LDPC_CUDA_TRY(cudaFuncSetAttribute(nb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     LDPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nb_decode_kernel, threads, smem));
