@@ -30,6 +30,9 @@
 //                         prefetch on top of it LOSES 2 %
 //   LDPC_REC_PREFETCH  0  1 = prefetch.global.L1, 2 = prefetch.global.L2 of the next step's record at row start
 //   LDPC_PARITY_XOR    1  sign parity as xor of the t patterns (LOP3) instead of an fp16 count (9.30 -> 9.06 ms)
+//   LDPC_NEG_ALU       1  (t < 0) as HSET2 on the ALU pipe instead of fma.sat on the FMA pipe: after the rework the
+//                         fp16 FMA pipe is the fuller one (8.76 -> 8.63 ms); moving the sign shifts to the ALU pipe
+//                         (SHF instead of IMAD.SHL) or phase 2's sign product to the FMA pipe both LOSE
 //   LDPC_LOAD_DEPTH    8  channel-value vectors in flight per thread in the load phase
 //   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values (on: evicts records, +4 %)
 #ifndef LDPC_L2_PREFETCH
@@ -43,6 +46,9 @@
 #endif
 #ifndef LDPC_REC_PRELOAD
 #define LDPC_REC_PRELOAD 2
+#endif
+#ifndef LDPC_NEG_ALU
+#define LDPC_NEG_ALU 1
 #endif
 #ifndef LDPC_LOAD_DEPTH
 #define LDPC_LOAD_DEPTH 8
@@ -187,7 +193,7 @@ __host__ __device__ constexpr int sign_bit_pos(int dc, int k)
 //    accumulator pair per set of 8 edges; the amax clamp commutes with the minimum and is applied to
 //    the keys once per row (key1 -> min(key1, 8*amax) also yields the oracle's "first index" when every
 //    |t| saturates).  Keys are decoded (floor(key/8), key mod 8) on the FMA pipe.
-//  * sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)), (t<0) = fma.sat(t, -1, 0).
+//  * sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)); (t<0) is an HSET2 (LDPC_NEG_ALU) or fma.sat(t, -1, 0).
 // Pipe balance (ncu: the ALU pipe was the binding one, profiles/r01_*): per edge and pair of frames the
 // ALU pipe sees PRMT, HSET2.EQ, LOP3, 2.5 x VIMNMX in phase 1 and HSET2.EQ, LOP3, VIADDMNMX in phase 2;
 // everything else (selects, sign/parity collection, keys, decode, beta scaling) is HFMA2 / HADD2 / IMAD.
@@ -269,7 +275,7 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
                 }
                 tp[h][k] = t1;
                 const __half2 tt = __hsub2(t1, kbias);
-                const __half2 neg = neg01(tt);  // 1.0 where t < 0
+                const __half2 neg = LDPC_NEG_ALU ? __hlt2(tt, zero) : neg01(tt);  // 1.0 where t < 0
                 sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
                 if (LDPC_PARITY_XOR)
                     par[h] ^= h2u(tt);
