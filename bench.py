@@ -34,8 +34,8 @@ EBN0_DB = 2.0
 # B_cw(it) = it*(2*E*w + 2*M*rec) + N*4 + N/8, int8: w = 1, rec = 4  -> 4 638 400 B at 10 it
 B_CW = ITERS * (2 * E * 1 + 2 * M * 4) + N * 4 + N // 8
 # dram__bytes_read.sum + dram__bytes_write.sum of one ldpc_layered_i8_kernel launch over 2368 frames, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_layered_i8_summary.txt (1.60 GB + 3.29 GB): per frame
-NCU_DRAM_BYTES_PER_FRAME = (1.596703e9 + 3.285236e9) / 2368
+# `ncu --set full` capture summarised in profiles/r01_ncu_layered_i8_summary.txt (1.49 GB + 3.29 GB): per frame
+NCU_DRAM_BYTES_PER_FRAME = (1.486490e9 + 3.289583e9) / 2368
 METRIC = "decoded info Gbit/s at fixed iters"
 WORKLOAD = ("binary QC-LDPC J15_L30_Z1280 (N=38400, K=19200), BPSK-AWGN Eb/N0 2.0 dB, layered normalised "
             "min-sum (x0.875), int8 state, 10 iterations fixed, no early exit")
@@ -296,7 +296,7 @@ def run_ours(args):
                                         "streaming layered decoder).  This design keeps the APP state in shared "
                                         "memory, so its real DRAM traffic is lower (traffic) and the pipe that binds is "
                                         "the SM issue rate, not HBM: see issue_bound",
-                         "issue_bound": {"inst_per_edge_4frames": 57.5, "ipc_per_smsp": 0.70,
+                         "issue_bound": {"inst_per_edge_4frames": 57.5, "ipc_per_smsp": 0.71,
                                          "practical_ipc_peak_per_smsp": 0.80,
                                          "source": "profiles/r01_ncu_layered_i8_summary.txt, profiles/r01_pipe_ubench.txt"}},
         }
