@@ -324,6 +324,13 @@ __device__ void ems_check_row_full_warp(const NbParams &p, int row, int d0, int 
     }
 }
 
+// order-preserving float -> uint map (x + 0.0f folds -0 into +0 first), for warp reductions with redux.sync
+__device__ __forceinline__ unsigned ord_key(float x)
+{
+    const unsigned u = __float_as_uint(__fadd_rn(x, 0.0f));
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
 // (value, list position) order of the stable descending sort of [1, 2, ..., q-1, 0] (BubleSort :17-36)
 __device__ __forceinline__ bool ems_before(float xa, int ia, float xb, int ib) { return xa > xb || (xa == xb && ia < ib); }
 
@@ -360,16 +367,12 @@ __device__ void ems_var_node_warp(const NbParams &p, int col, const float *lch, 
             llr[t] = 0.0f;
         }
     }
-    // warp argmax, lowest symbol on ties (the serial scan keeps the first strict maximum)
-    for (int o = 16; o > 0; o >>= 1) {
-        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-        if (omx > mx || (omx == mx && ob < best)) {
-            mx = omx;
-            best = ob;
-        }
+    // warp argmax, lowest symbol on ties (the serial scan keeps the first strict maximum): two redux.sync
+    {
+        const unsigned key = ord_key(mx), wk = __reduce_max_sync(0xffffffffu, key);
+        best = (int)__reduce_min_sync(0xffffffffu, key == wk ? (unsigned)best : 0xffffffffu);
+        if (lane == 0) sym[col] = (uint16_t)((wk <= ord_key(0.0f)) ? 0 : best);
     }
-    if (lane == 0) sym[col] = (uint16_t)((mx <= 0.0f) ? 0 : best);
 #pragma unroll
     for (int d = 0; d < dv; d++) {
         const int e = col * p.dv_max + d;
@@ -394,16 +397,11 @@ __device__ void ems_var_node_warp(const NbParams &p, int col, const float *lch, 
                     bt = t;
                 }
             }
-            float wx = bx;
-            int wi = bi;
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ox = __shfl_xor_sync(0xffffffffu, wx, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-                if (oi != 0x7fffffff && (wi == 0x7fffffff || ems_before(ox, oi, wx, wi))) {
-                    wx = ox;
-                    wi = oi;
-                }
-            }
+            // warp winner: largest value, smallest list position among equals — one redux.sync each
+            const unsigned key = bt >= 0 ? ord_key(bx) : 0u;
+            const unsigned wk = __reduce_max_sync(0xffffffffu, key);
+            const int wi = (int)__reduce_min_sync(0xffffffffu, (bt >= 0 && key == wk) ? (unsigned)bi : 0x7fffffffu);
+            const float wx = bx;
             if (bt >= 0 && bi == wi) {  // this lane holds the winner: retire it and publish
 #pragma unroll
                 for (int t = 0; t < kMaxPerLane; t++)
