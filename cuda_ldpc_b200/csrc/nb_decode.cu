@@ -585,12 +585,17 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
             Ii = m1a;
             p0 = p1 = s.MinCol[a];
             bool two = false;
+            // The pairs {j, a ^ j} and {a ^ j, j} carry the same max(d1, d2); the serial scan meets the smaller
+            // index first and the later visit can never pass the strict "<", so only j < (a ^ j) is walked: the
+            // numbers whose bit msb(a) is clear, in ascending order.  (j = a is the partner of j = 0 and skipped.)
+            const int hb = 31 - __clz(a), lowm = (1 << hb) - 1;
 #pragma unroll 4
-            for (int j = 0; j < q; j++) {
+            for (int t = 0; t < q / 2; t++) {
+                const int j = ((t >> hb) << (hb + 1)) | (t & lowm);
                 const int2 ej = s.MC[j], ek = s.MC[a ^ j];
                 const float d1 = __int_as_float(ej.x), d2 = __int_as_float(ek.x);
                 const float m = fmaxf(d1, d2);
-                if (j != a && ej.y != ek.y && d1 != d2 && m < Ii) {
+                if (ej.y != ek.y && d1 != d2 && m < Ii) {
                     Ii = m;
                     p0 = ej.y;
                     p1 = ek.y;
