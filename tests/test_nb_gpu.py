@@ -326,3 +326,32 @@ def test_log_qspa_full_configuration_set(nb_oracle, gf_dir, meta):
     _, _, ok_full = code.decode(rxs, 20, algo=m.ALGO_EMS, in_kind=m.IN_BPSK, sigma=sigma2, ems_nm=q, ems_nc=dc_max - 1)
     _, _, ok_22 = code.decode(rxs, 20, algo=m.ALGO_EMS, in_kind=m.IN_BPSK, sigma=sigma2)
     assert ok_full.sum() >= ok_22.sum() - 1 and ok_full.sum() >= 16
+
+
+@pytest.mark.parametrize("name,exp,snr,algo", [("C4", 1, 13.0, "ALGO_EMS"), ("C4", 1, 13.0, "ALGO_LAYERED_TMM"),
+                                               ("C5", 1, 7.0, "ALGO_TMM"), ("C5", 1, 7.0, "ALGO_FFT_BP")])
+def test_large_batch_properties(meta, name, exp, snr, algo):
+    """Bench-sized batches (device path, Philox channel): at a comfortable SNR every frame of the all-zero word
+    converges to the all-zero word, the result does not depend on how the batch is cut into calls, and a second
+    decode of the same samples is identical (no state leaks between frames or calls)."""
+    import torch
+    cfg = meta["configs"][name]
+    code = m.NbLdpcCode(os.path.join(NB_DATA, cfg["matrix"]), None,
+                        os.path.join(NB_DATA, cfg["constellation"].replace("./", "")), coef_is_exponent=bool(exp))
+    F = 8192 if name == "C4" else 2048
+    kind = m.IN_BPSK if cfg["n_qam"] == 2 else m.IN_QAM
+    per = code.in_elems(kind)
+    sigma = m.lib.nb_ldpc_sigma(code._h, 0, snr, 0)
+    x = torch.empty(F * per, dtype=torch.float32, device="cuda")
+    rc = m.lib.nb_ldpc_modulate_awgn(code._h, x.data_ptr(), F, sigma, 7, 0, None, torch.cuda.current_stream().cuda_stream)
+    assert rc >= 0
+    x = x.view(F, per)
+    a = getattr(m, algo)
+    out, it, ok = code.decode(x, 20, algo=a, in_kind=kind, sigma=sigma)
+    assert int(ok.sum()) == F and int(out.abs().sum()) == 0
+    out2, it2, ok2 = code.decode(x, 20, algo=a, in_kind=kind, sigma=sigma)
+    assert torch.equal(out, out2) and torch.equal(it, it2)
+    h = F // 2 + 37  # ragged split
+    o_a, i_a, _ = code.decode(x[:h].contiguous(), 20, algo=a, in_kind=kind, sigma=sigma)
+    o_b, i_b, _ = code.decode(x[h:].contiguous(), 20, algo=a, in_kind=kind, sigma=sigma)
+    assert torch.equal(torch.cat([o_a, o_b]), out) and torch.equal(torch.cat([i_a, i_b]), it)
