@@ -447,6 +447,10 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
             LDPC_ROWS((DCHI >= 3 ? DCHI - 2 : 1))
         } else if (DCHI >= 4 && dc == DCHI - 3) {
             LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
+        } else if (DCHI >= 5 && dc == DCHI - 4) {  // six exact degrees per bucket: every shipped code whose
+            LDPC_ROWS((DCHI >= 5 ? DCHI - 4 : 1))  // degrees spread over two values stays on the exact paths
+        } else if (DCHI >= 6 && dc == DCHI - 5) {  // (J20 / J40 / J48_L60_Z160 ran 2x slower through the generic one)
+            LDPC_ROWS((DCHI >= 6 ? DCHI - 5 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
             generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, nxl, pf_next_layer, amax8, amax8p7, bmul, nbias);
             if (LDPC_REC_PRELOAD && pf_next_layer && tid < Z) rec_load<RecLayout<DCHI>::U4>(nxl + (size_t)tid * RS, rw);
