@@ -185,6 +185,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "unset"
+    try:  # run on (and allocate pinned host buffers from) the CPUs next to this GPU: the e2e copies stay NUMA-local
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = f"{len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:  # affinity is an optimisation only
+        numa = f"unavailable ({type(e).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", CODE_FILE))
@@ -281,6 +289,7 @@ def run_ours(args):
                        "converged_fraction": ok_frac},
             "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": Fe, "steps": e2e_steps, "launches_per_step": launches_e2e,
+                    "cpu_affinity": numa,
                     "layout": "[N][F] fp32 pinned host buffer (the reference's Channel_Out layout); the library cuts "
                               "the batch into chunks of 2 groups per SM on two streams (H2D / decode / D2H overlap)",
                     "rank0_value_with_FN_layout_chunked_overlap": e2e_fn_val},
@@ -300,6 +309,10 @@ def run_ours(args):
                                          "practical_ipc_peak_per_smsp": 0.80,
                                          "source": "profiles/r01_ncu_layered_i8_summary.txt, profiles/r01_pipe_ubench.txt"}},
         }
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline uses every host core again
+        except Exception:
+            pass
         try:
             line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_port()
         except Exception as e:  # the bench value never depends on the oracle
