@@ -273,6 +273,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_fn_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
     del yh_fn
+    # and with host-side int8 packing of the chunks (ldpc_decode_opts_t::host_pack_threads): a quarter of the PCIe
+    # bytes, same bits, but it occupies the host cores — informational; only tried when this rank has >= 12 of them
+    pack_threads = (os.cpu_count() or 1) // world
+    e2e_pack_val = None
+    if pack_threads >= 12:
+        code.decode(yh, ITERS, host_pack_threads=pack_threads, **hkw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            code.decode(yh, ITERS, host_pack_threads=pack_threads, **hkw)
+        torch.cuda.synchronize()
+        e2e_pack_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
     clk.__exit__()
 
     if rank == 0:
@@ -292,7 +304,8 @@ def run_ours(args):
                     "cpu_affinity": numa,
                     "layout": "[N][F] fp32 pinned host buffer (the reference's Channel_Out layout); the library cuts "
                               "the batch into chunks of 2 groups per SM on two streams (H2D / decode / D2H overlap)",
-                    "rank0_value_with_FN_layout_chunked_overlap": e2e_fn_val},
+                    "rank0_value_with_FN_layout_chunked_overlap": e2e_fn_val,
+                    "rank0_value_with_host_int8_packing": e2e_pack_val, "host_pack_threads": pack_threads},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

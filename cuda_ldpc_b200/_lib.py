@@ -22,7 +22,7 @@ class DecodeOpts(C.Structure):
         ("beta_num", C.c_int), ("beta_shift", C.c_int), ("iters_out", C.c_void_p), ("ok_out", C.c_void_p),
         ("stream", C.c_void_p), ("debug_app", C.c_void_p), ("debug_msgs", C.c_void_p),
         ("channel_sigma", C.c_float), ("channel_seed", C.c_uint64), ("channel_first_frame", C.c_uint64),
-        ("channel_codeword", C.c_void_p),
+        ("channel_codeword", C.c_void_p), ("host_pack_threads", C.c_int),
     ]
 
 

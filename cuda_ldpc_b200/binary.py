@@ -124,10 +124,10 @@ class LdpcCode:
 
     def decode(self, llr, iters, *, schedule=SCHED_FLOODING, msg_dtype=None, layout=LAYOUT_NF, early_exit=EXIT_NONE,
                out_format=OUT_INT32_REF, alpha=1.0, llr_scale=8.0, msg_max=127, beta_num=0, beta_shift=0,
-               stream=None, debug=False, out=None, iters_out=None, ok_out=None):
+               stream=None, debug=False, out=None, iters_out=None, ok_out=None, host_pack_threads=0):
         """llr: numpy array (host path: copies in/out, synchronises) or torch CUDA tensor (device
         path: enqueues on `stream` / the current torch stream).  Shape [N, F] (LAYOUT_NF) or
-        [F, N] (LAYOUT_FN)."""
+        [F, N] (LAYOUT_FN).  host_pack_threads: see ldpc_decode_opts_t (host path, layered int8)."""
         if msg_dtype is None:
             msg_dtype = DTYPE_FP32 if schedule == SCHED_FLOODING else DTYPE_INT8
         N = self.N
@@ -203,7 +203,7 @@ class LdpcCode:
         o = self.make_opts(F, layout=layout, llr_dtype=dt, mem_space=MEM_HOST, schedule=schedule, msg_dtype=msg_dtype,
                            early_exit=early_exit, out_format=out_format, alpha=alpha, llr_scale=llr_scale,
                            msg_max=msg_max, beta_num=beta_num, beta_shift=beta_shift, iters_out=it.ctypes.data,
-                           ok_out=ok.ctypes.data, stream=stream,
+                           ok_out=ok.ctypes.data, stream=stream, host_pack_threads=int(host_pack_threads),
                            debug_app=app.ctypes.data if app is not None else None,
                            debug_msgs=msgs.ctypes.data if msgs is not None else None)
         rc = lib.ldpc_decode_batch(self._h, a.ctypes.data, outb.ctypes.data, int(iters), C.byref(o))

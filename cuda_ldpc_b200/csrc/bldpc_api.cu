@@ -5,6 +5,7 @@
 // (:38-88, :160-163), nothing is copied to the host per iteration (:135) and errors are
 // returned, not printed.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -93,11 +94,37 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // EVERY iteration, B/Simulation.cu:138, B/LDPC_Decoder.cu:135).  A [N][F] chunk is a strided column
 // block (cudaMemcpy2DAsync), a [F][N] chunk is contiguous.  Pinned host memory (inputs AND result
 // buffers) is needed for real overlap; pageable memory still works (the copies then serialise).
+extern "C" void ldpcb_host_pack_nf(const float *y, size_t ldF, int N, int f0, int fc, float scale, signed char *out,
+                                   int threads);  // host_pack.cc
+
+// pinned staging slots of the host-pack path, grown on demand
+static int ensure_pack_slots(const ldpc_code *cc, size_t bytes)
+{
+    ldpc_code *c = const_cast<ldpc_code *>(cc);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    for (int i = 0; i < 2; i++)
+        if (!c->pack_ev[i]) LDPC_CUDA_TRY(cudaEventCreateWithFlags(&c->pack_ev[i], cudaEventDisableTiming));
+    if (c->pack_host_bytes >= bytes) return LDPC_OK;
+    for (int i = 0; i < 2; i++) {
+        if (c->pack_host[i]) LDPC_CUDA_TRY(cudaFreeHost(c->pack_host[i]));
+        c->pack_host[i] = nullptr;
+        LDPC_CUDA_TRY(cudaHostAlloc(&c->pack_host[i], bytes, cudaHostAllocDefault));
+    }
+    c->pack_host_bytes = bytes;
+    return LDPC_OK;
+}
+
 static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard_bits, int iters,
                                  const ldpc_decode_opts_t *o, int Fc)
 {
     const int F = o->batch, N = c->N;
-    const size_t esz = dtype_bytes(o->llr_dtype);
+    // host pack: fp32 [N][F] -> int8 chunk on host threads, a quarter of the PCIe bytes, same decode bit for bit
+    const bool pack = o->host_pack_threads >= 1 && o->llr_dtype == LDPC_DTYPE_FP32 && o->layout == LDPC_LAYOUT_NF;
+    if (pack) {
+        int rcp = ensure_pack_slots(c, (size_t)N * Fc);
+        if (rcp != LDPC_OK) return rcp;
+    }
+    const size_t esz = pack ? 1 : dtype_bytes(o->llr_dtype);
     const int W = (N + 31) / 32;
     size_t rec_bytes = 0;
     int rc = layered_i8_scratch_bytes(c, Fc, o->beta_num, &rec_bytes);
@@ -117,7 +144,16 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
         unsigned char *d_in = sl, *d_out = sl + in_b;
         int *d_it = reinterpret_cast<int *>(sl + in_b + out_b), *d_ok = reinterpret_cast<int *>(sl + in_b + out_b + fl_b);
         const unsigned char *h_in = reinterpret_cast<const unsigned char *>(llr);
-        if (o->layout == LDPC_LAYOUT_NF)
+        if (pack) {
+            // the slot was last read by the copy of chunk k-2: wait for it, quantise chunk k into it (the GPU is
+            // busy with chunk k-1 meanwhile), copy the contiguous [N][fc] block
+            if (k >= 2) LDPC_CUDA_TRY(cudaEventSynchronize(c->pack_ev[k & 1]));
+            signed char *stage = reinterpret_cast<signed char *>(c->pack_host[k & 1]);
+            ldpcb_host_pack_nf(reinterpret_cast<const float *>(llr), (size_t)F, N, f0, fc, o->llr_scale, stage,
+                               o->host_pack_threads);
+            LDPC_CUDA_TRY(cudaMemcpyAsync(d_in, stage, (size_t)N * fc, cudaMemcpyHostToDevice, st));
+            LDPC_CUDA_TRY(cudaEventRecord(c->pack_ev[k & 1], st));
+        } else if (o->layout == LDPC_LAYOUT_NF)
             LDPC_CUDA_TRY(cudaMemcpy2DAsync(d_in, (size_t)fc * esz, h_in + (size_t)f0 * esz, (size_t)F * esz,
                                             (size_t)fc * esz, N, cudaMemcpyHostToDevice, st));
         else
@@ -125,7 +161,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
                                           cudaMemcpyHostToDevice, st));
         LayeredArgs a;
         a.llr = d_in;
-        a.llr_dtype = o->llr_dtype;
+        a.llr_dtype = pack ? LDPC_DTYPE_INT8 : o->llr_dtype;
         a.layout = o->layout;
         a.F = fc;
         a.iters = iters;
@@ -232,7 +268,8 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     // the bench workload (1.45 GB of fp32 per call, pinned): 37.9 ms unchunked -> 28.5 ms with 8 chunks,
     // i.e. PCIe-bound (55 GB/s) instead of copy + decode in series (profiles/r01_h2d_probe.txt).
     if (host && !flooding && !fused_channel && o->msg_dtype == LDPC_DTYPE_INT8 && !o->debug_app && !o->debug_msgs) {
-        const int Fc = 4 * c->num_sms * 2;
+        int Fc = 4 * c->num_sms * 2;
+        if (const char *e = getenv("LDPC_B200_CHUNK_GROUPS")) Fc = 4 * c->num_sms * (atoi(e) > 0 ? atoi(e) : 2);  // tuning
         if (F >= 2 * Fc) return decode_host_pipelined(c, llr, hard_bits, iters, o, Fc);
     }
     const size_t in_bytes = fused_channel ? 0 : (size_t)c->N * F * dtype_bytes(o->llr_dtype);

@@ -632,8 +632,27 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 }
             }
         }
+        // int8 [N][F], whole group: the 4 frames of a code bit are one aligned 32-bit word (the host-pack path of
+        // ldpc_decode_batch feeds this); byte s -> max(s, -127) + 127 without unpacking
+        const bool fast_load8 = LDPC_LOAD_DEPTH > 1 && p.llr_dtype == LDPC_DTYPE_INT8 && p.layout == LDPC_LAYOUT_NF &&
+                                valid == 0xFu && (F & 3) == 0 && (reinterpret_cast<size_t>(p.llr) & 3) == 0;
+        if (fast_load8) {
+            constexpr int kLoadDepth = LDPC_LOAD_DEPTH;
+            const unsigned *y1 = reinterpret_cast<const unsigned *>(reinterpret_cast<const signed char *>(p.llr) + f0);
+            const size_t st1 = (size_t)(F >> 2);
+            for (int n0 = tid; n0 < N; n0 += kLoadDepth * T) {
+                unsigned v[kLoadDepth];
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) v[u] = __ldg(y1 + (size_t)min(n0 + u * T, N - 1) * st1);
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) {
+                    const int n = n0 + u * T;
+                    if (n < N) appw[n] = __vmaxu4(v[u] ^ 0x80808080u, 0x01010101u) - 0x01010101u;
+                }
+            }
+        }
 #pragma unroll 2
-        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL || fast_load) ? N : tid; n < N; n += T) {
+        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL || fast_load || fast_load8) ? N : tid; n < N; n += T) {
             int q[4];
             if (p.llr_dtype == LDPC_DTYPE_FP32) {
                 const float *y = reinterpret_cast<const float *>(p.llr);

@@ -125,6 +125,9 @@ extern "C" int ldpc_load_code(const char *path, int J, int L, int Z, ldpc_code_t
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     c->pipe_stream[0] = c->pipe_stream[1] = nullptr;
+    c->pack_host[0] = c->pack_host[1] = nullptr;
+    c->pack_host_bytes = 0;
+    c->pack_ev[0] = c->pack_ev[1] = nullptr;
     c->enc_state = 0;
     memset(&c->lt, 0, sizeof(c->lt));
     memset(&c->ct, 0, sizeof(c->ct));
@@ -188,8 +191,11 @@ extern "C" void ldpc_free_code(ldpc_code_t *code)
 {
     if (!code) return;
     if (code->scratch) cudaFree(code->scratch);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++) {
         if (code->pipe_stream[i]) cudaStreamDestroy(code->pipe_stream[i]);
+        if (code->pack_host[i]) cudaFreeHost(code->pack_host[i]);
+        if (code->pack_ev[i]) cudaEventDestroy(code->pack_ev[i]);
+    }
     delete code;
 }
 

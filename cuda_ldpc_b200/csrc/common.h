@@ -63,6 +63,10 @@ struct ldpc_code {
     size_t scratch_bytes;
     // two internal streams for the chunked host path (H2D of chunk k+1 under the decode of chunk k)
     cudaStream_t pipe_stream[2];
+    // pinned int8 staging slots + "slot free again" events of the host-pack path (ldpc_decode_opts_t::host_pack_threads)
+    void *pack_host[2];
+    size_t pack_host_bytes;
+    cudaEvent_t pack_ev[2];
     // encoder cache (host): parity-part inverse, built lazily
     std::vector<uint32_t> enc_cache;
     int enc_state;  // 0 = not built, 1 = ok, -1 = singular

@@ -202,6 +202,29 @@ def test_chunked_host_path_equals_device_path(oracle, layout, fmt):
     assert (rh.D == (got.view(np.uint32) if fmt == m.OUT_BITPACK else got)).all()
     assert (rh.iters == rd.iters.cpu().numpy()).all() and (rh.ok == rd.ok.cpu().numpy()).all()
     assert rh.launches == 3 and rd.launches == 1
+    # host pack: the chunks quantised to int8 on host threads before the copy — same result bit for bit
+    rp = code.decode(yy, 10, host_pack_threads=3, **kw)
+    assert (rp.D == rh.D).all() and (rp.iters == rh.iters).all() and (rp.ok == rh.ok).all() and rp.launches == 3
+
+
+def test_host_pack_extreme_values(oracle):
+    """Quantisation on the host must follow the kernel's rule everywhere: ties to even, saturation at +-127,
+    huge and tiny values, and a batch that is a multiple of 4 per chunk edge case."""
+    import torch
+    code, _ = load(oracle, "C1")
+    F = 2 * 4 * 148 * 2 + 8  # chunked path with a short last chunk
+    rng = np.random.default_rng(5)
+    y = (rng.standard_normal((code.N, F)) * 3.0).astype(np.float32)
+    special = np.array([0.0625, -0.0625, 0.1875, -0.1875, 0.3125, 15.875, 15.9375, -15.9375, 1e9, -1e9, 1e-30, -1e-30,
+                        15.8125, -15.8125, 0.0, -0.0], np.float32)
+    y[:special.size, 0] = special
+    y[1, : special.size] = special
+    kw = dict(schedule=m.SCHED_LAYERED, out_format=m.OUT_BITPACK, msg_max=127, llr_scale=8.0, early_exit=m.EXIT_NONE)
+    ra = code.decode(y, 3, **kw)
+    rb = code.decode(y, 3, host_pack_threads=4, debug=False, **kw)
+    assert (ra.D == rb.D).all() and (ra.ok == rb.ok).all()
+    rd = code.decode(torch.as_tensor(y, device="cuda"), 3, **kw)
+    assert (rd.D.cpu().numpy().view(np.uint32) == rb.D).all()
 
 
 ALL_FILES = sorted(f for f in os.listdir(BL) if f.endswith(".txt"))
