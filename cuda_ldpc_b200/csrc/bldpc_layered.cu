@@ -194,9 +194,12 @@ __host__ __device__ constexpr int sign_bit_pos(int dc, int k)
 //    the keys once per row (key1 -> min(key1, 8*amax) also yields the oracle's "first index" when every
 //    |t| saturates).  Keys are decoded (floor(key/8), key mod 8) on the FMA pipe.
 //  * sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)); (t<0) is an HSET2 (LDPC_NEG_ALU) or fma.sat(t, -1, 0).
-// Pipe balance (ncu: the ALU pipe was the binding one, profiles/r01_*): per edge and pair of frames the
-// ALU pipe sees PRMT, HSET2.EQ, LOP3, 2.5 x VIMNMX in phase 1 and HSET2.EQ, LOP3, VIADDMNMX in phase 2;
-// everything else (selects, sign/parity collection, keys, decode, beta scaling) is HFMA2 / HADD2 / IMAD.
+// Pipe balance (profiles/r01_pipe_ubench.txt: every instruction here issues once per 2 cycles per sub-partition,
+// HFMA2 / HADD2 / IMAD on one pipe, HSET2 / VIMNMX / LOP3 / PRMT on the other, ~0.8 IPC at best when mixed): per
+// edge and pair of frames the ALU pipe sees PRMT, HSET2.EQ, LOP3, HSET2.LT, 2.5 x VIMNMX, 0.5 x LOP3 (parity) in
+// phase 1 and HSET2.EQ, LOP3, VIADDMNMX in phase 2; the FMA pipe the select HFMA2, IMAD.SHL, two HADD2, the sign
+// and key HFMA2 in phase 1 and HFMA2, IMAD.SHL, HADD2 in phase 2, plus decode / beta scaling per row.  A/B runs
+//  put the optimum at this split: moving one more op either way loses.
 __device__ __forceinline__ __half2 neg01(__half2 t)
 {
     unsigned d;
