@@ -135,6 +135,33 @@ def test_layered_i8_scaling_and_clipping_variants(oracle, bnum, bshift, amax, sc
     assert (r.app == app).all() and (r.msgs == rec).all() and (r.D == D).all()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_layered_i8_randomised_settings(oracle, seed):
+    """Seeded sweep over code, quantiser scale, message clip, beta and SNR (heavy saturation included): APP values,
+    check records (min1, min2, first index, signs), hard bits and iteration counts against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    key = ["C1", "C3", "J32", "J6", "J10", "C2"][seed % 6]
+    code, oc = load(oracle, key)
+    for _ in range(3):
+        bshift = int(rng.integers(1, 6))
+        bnum = int(rng.integers(0, min(8, (1 << bshift) - 1) + 1))
+        amax = int(rng.choice([1, 3, 7, 15, 31, 63, 100, 127]))
+        scale = float(rng.choice([0.5, 2.0, 8.0, 16.0, 64.0]))  # 64: almost every LLR saturates
+        snr = float(rng.uniform(-1.0, 4.0))
+        it = int(rng.integers(1, 7))
+        mode = int(rng.choice([m.EXIT_NONE, m.EXIT_SYNDROME]))
+        F = int(rng.choice([3, 8, 17])) if key != "C2" else 5
+        y = noisy(oracle, code.N, F, snr)
+        r = code.decode(y, it, schedule=m.SCHED_LAYERED, early_exit=mode, debug=True, beta_num=bnum, beta_shift=bshift,
+                        msg_max=amax, llr_scale=scale)
+        D, its, app, rec = orc_i8(oracle, oc, y, it, mode, scale, amax, bnum, bshift)
+        tag = (key, bnum, bshift, amax, scale, snr, it, mode, F)
+        assert (r.iters == its).all(), tag
+        assert (r.app == app).all(), tag
+        assert (r.msgs == rec).all(), tag
+        assert (r.D == D).all(), tag
+
+
 def test_layered_i8_io_variants(oracle):
     code, oc = load(oracle, "C3")
     F = 10
