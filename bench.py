@@ -273,6 +273,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_fn_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
     del yh_fn
+    # context for "PCIe-bound": the same call fed fp16 channel values (half the bytes; NOT the reference's input type)
+    yh16 = torch.from_numpy(yh).to(torch.float16).pin_memory().numpy()
+    code.decode(yh16, ITERS, **hkw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        code.decode(yh16, ITERS, **hkw)
+    torch.cuda.synchronize()
+    e2e_fp16_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
+    del yh16
     # and with host-side int8 packing of the chunks (ldpc_decode_opts_t::host_pack_threads): a quarter of the PCIe
     # bytes, same bits, but it occupies the host cores — informational; only tried when this rank has >= 12 of them
     pack_threads = (os.cpu_count() or 1) // world
@@ -305,7 +315,8 @@ def run_ours(args):
                     "layout": "[N][F] fp32 pinned host buffer (the reference's Channel_Out layout); the library cuts "
                               "the batch into chunks of 2 groups per SM on two streams (H2D / decode / D2H overlap)",
                     "rank0_value_with_FN_layout_chunked_overlap": e2e_fn_val,
-                    "rank0_value_with_host_int8_packing": e2e_pack_val, "host_pack_threads": pack_threads},
+                    "rank0_value_with_host_int8_packing": e2e_pack_val, "host_pack_threads": pack_threads,
+                    "rank0_value_with_fp16_host_input": e2e_fp16_val},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

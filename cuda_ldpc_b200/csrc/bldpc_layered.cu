@@ -635,6 +635,29 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 }
             }
         }
+        // fp16 [N][F], whole group: one aligned 8-byte vector per code bit (same rule as fp32 after the exact
+        // half -> float conversion)
+        const bool fast_load16 = LDPC_LOAD_DEPTH > 1 && p.llr_dtype == LDPC_DTYPE_FP16 && p.layout == LDPC_LAYOUT_NF &&
+                                 valid == 0xFu && (F & 3) == 0 && (reinterpret_cast<size_t>(p.llr) & 7) == 0;
+        if (fast_load16) {
+            constexpr int kLoadDepth = LDPC_LOAD_DEPTH;
+            const uint2 *y2 = reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(p.llr) + f0);
+            const size_t st2 = (size_t)(F >> 2);
+            for (int n0 = tid; n0 < N; n0 += kLoadDepth * T) {
+                uint2 v[kLoadDepth];
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) v[u] = __ldg(y2 + (size_t)min(n0 + u * T, N - 1) * st2);
+#pragma unroll
+                for (int u = 0; u < kLoadDepth; u++) {
+                    const int n = n0 + u * T;
+                    if (n < N) {
+                        const float2 a = __half22float2(u2h(v[u].x)), b = __half22float2(u2h(v[u].y));
+                        appw[n] = (unsigned)(quant(a.x, p.scale) + 127) | ((unsigned)(quant(a.y, p.scale) + 127) << 8) |
+                                  ((unsigned)(quant(b.x, p.scale) + 127) << 16) | ((unsigned)(quant(b.y, p.scale) + 127) << 24);
+                    }
+                }
+            }
+        }
         // int8 [N][F], whole group: the 4 frames of a code bit are one aligned 32-bit word (the host-pack path of
         // ldpc_decode_batch feeds this); byte s -> max(s, -127) + 127 without unpacking
         const bool fast_load8 = LDPC_LOAD_DEPTH > 1 && p.llr_dtype == LDPC_DTYPE_INT8 && p.layout == LDPC_LAYOUT_NF &&
@@ -655,7 +678,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             }
         }
 #pragma unroll 2
-        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL || fast_load || fast_load8) ? N : tid; n < N; n += T) {
+        for (int n = (p.llr_dtype == LDPC_DTYPE_CHANNEL || fast_load || fast_load8 || fast_load16) ? N : tid; n < N; n += T) {
             int q[4];
             if (p.llr_dtype == LDPC_DTYPE_FP32) {
                 const float *y = reinterpret_cast<const float *>(p.llr);

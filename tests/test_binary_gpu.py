@@ -178,6 +178,27 @@ def test_layered_i8_io_variants(oracle):
     assert (r.D == D[: code.N]).all()
 
 
+@pytest.mark.parametrize("F", [12, 13])
+def test_layered_i8_fp16_and_int8_inputs_match_fp32(oracle, F):
+    """fp16 and int8 channel values in the [N][F] layout (vector fast paths when F is a multiple of 4, scalar
+    path otherwise), host and device buffers: same decode as the fp32 input holding the same values."""
+    import torch
+    code, oc = load(oracle, "C1")
+    y16 = noisy(oracle, code.N, F, 2.8).astype(np.float16)
+    kw = dict(schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=m.OUT_U8, msg_max=31, beta_num=1, beta_shift=3)
+    want = code.decode(y16.astype(np.float32), 8, **kw)
+    for got in (code.decode(y16, 8, **kw), code.decode(torch.as_tensor(y16, device="cuda"), 8, **kw)):
+        D = got.D if isinstance(got.D, np.ndarray) else got.D.cpu().numpy()
+        it = got.iters if isinstance(got.iters, np.ndarray) else got.iters.cpu().numpy()
+        assert (D == want.D).all() and (it == want.iters).all()
+    q = np.clip(np.rint(y16.astype(np.float32) * 8), -128, 127).astype(np.int8)  # -128 must behave like -127
+    q[0, 0] = -128
+    want8 = code.decode(np.maximum(q, -127).astype(np.float32) / 8, 8, **kw)
+    for got in (code.decode(q, 8, **kw), code.decode(torch.as_tensor(q, device="cuda"), 8, **kw)):
+        D = got.D if isinstance(got.D, np.ndarray) else got.D.cpu().numpy()
+        assert (D == want8.D).all()
+
+
 def test_device_path_and_large_batch_properties(oracle):
     """Device-resident I/O (torch tensors, no host copies) at a batch that fills the GPU; size-
     independent checks: decoded words satisfy H x = 0 when flagged ok, equal frames decode equally,
