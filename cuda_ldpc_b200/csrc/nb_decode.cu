@@ -8,6 +8,7 @@
 // TMM bit-for-bit the reference's order), --fmad=false, the 1/1.2 and 0.8 scalings in double
 // like the reference (NB/src/LDPC_Decoder.cpp:309,519).
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -1056,6 +1057,14 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
                 slot_in_smem = 1;
                 break;
             }
+    // global-slot CTA widths from a sweep on B200 (ms per batch at T = 256 / 512 / 1024): C5 FFT-BP 15.0 / 12.3 / 11.8,
+    // C5 TMM 21.1 / 17.0 / 18.5, C4 TMM 6.4 / 6.6 / 7.0, C4 EMS 13.9 / 13.2 / 15.2
+    if (!slot_in_smem) {
+        if (o->algo == NB_ALGO_FFT_BP) threads = 4 * q > kNbThreadsMax ? kNbThreadsMax : (4 * q < kNbThreads ? kNbThreads : 4 * q);
+        if (o->algo == NB_ALGO_TMM && 2 * q > kNbThreads) threads = 2 * q > kNbThreadsMax ? kNbThreadsMax : 2 * q;
+        if (o->algo == NB_ALGO_EMS) threads = 512;
+        if ((work_floats_of(threads)) * sizeof(float) > kNbDynSmemMax) threads = kNbThreads;
+    }
     const size_t work_floats = work_floats_of(threads);
     const size_t smem = (work_floats + (slot_in_smem ? slot_floats : 0)) * sizeof(float);
     const int ems_chunk = threads / 32;
