@@ -1049,7 +1049,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
     // row-serial layered TMM runs one q-thread group per CTA (up to 32 CTAs per SM); FFT-BP, a chain of short
     // barrier-separated stages, is fastest as one wide CTA with the whole frame state in shared memory.
     int threads = kNbThreads, slot_in_smem = 0;
-    if (o->algo == NB_ALGO_LAYERED_TMM) threads = q < 64 ? 64 : ((q + 31) & ~31);
+    if (o->algo == NB_ALGO_LAYERED_TMM) threads = (q + 31) & ~31;  // one q-thread group, whole warps
     if (o->algo == NB_ALGO_FFT_BP)
         for (int T = kNbThreadsMax; T >= kNbThreads; T >>= 1)
             if ((work_floats_of(T) + slot_floats) * sizeof(float) <= kNbDynSmemMax) {
