@@ -561,7 +561,11 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned *appw = reinterpret_cast<unsigned *>(smem);
-    __shared__ unsigned s_fail;
+    // Syndrome fail bits of the CTA, ping-ponged by layer parity: layer r ORs into s_fail[r & 1] before the
+    // layer's barrier and every thread reads that word after it; the word is next written in layer r + 2, i.e.
+    // behind barrier r + 1, which no thread passes before all have read (a single word raced: a fast warp's
+    // atomicOr of layer r + 1 could reach a slow warp's read of layer r and split the CTA at the break below).
+    __shared__ unsigned s_fail[2];
     const int tid = threadIdx.x, T = blockDim.x;
     const int N = p.N, Z = p.Z, F = p.F, Z4 = 4 * Z;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
@@ -713,7 +717,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             appw[n] = (unsigned)(q[0] + 127) | ((unsigned)(q[1] + 127) << 8) | ((unsigned)(q[2] + 127) << 16) |
                       ((unsigned)(q[3] + 127) << 24);
         }
-        if (tid == 0) s_fail = 0u;
+        if (tid == 0) s_fail[0] = s_fail[1] = 0u;
         __syncthreads();
         // pull the channel values of this CTA's next group towards L2 while this group is decoded
         if (LDPC_L2_PREFETCH && !dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
@@ -744,13 +748,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                     unsigned fail = 0u;
                     for (int i = tid; i < Z; i += T) fail |= syndrome_row(smem, p, off, dc, 4 * i, Z4);
                     fail = __reduce_or_sync(0xffffffffu, fail);
-                    if ((tid & 31) == 0 && fail) atomicOr(&s_fail, fail);
+                    if ((tid & 31) == 0 && fail) atomicOr(&s_fail[r & 1], fail);
                     __syncthreads();
-                    fl = s_fail;
-                    if ((fl & rbytes) == rbytes) break;  // uniform: every thread reads the same word
+                    fl |= s_fail[r & 1];                 // words accumulate over layers r, r-2, ...: OR is idempotent
+                    if ((fl & rbytes) == rbytes) break;  // uniform: nobody writes this word before the next barrier
                 }
-                __syncthreads();
-                if (tid == 0) s_fail = 0u;
+                __syncthreads();  // every read of s_fail is done
+                if (tid == 0) s_fail[0] = s_fail[1] = 0u;  // next written behind the barriers of the next sweep
                 // okmask bit j = frame j satisfies all checks
                 const unsigned okmask = (((~fl) >> 7) & 1u) | (((~fl) >> 14) & 2u) | (((~fl) >> 21) & 4u) |
                                         (((~fl) >> 28) & 8u);
@@ -765,6 +769,10 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                             reinterpret_cast<int *>(p.out)[(size_t)N * F + f0 + tid] = (okmask >> tid) & 1u;
                     }
                     running &= ~finish;
+                    // `finish` is CTA-uniform.  The frames that keep running go straight into the next sweep, which
+                    // rewrites the APP words and records that write_outputs / dump_records of slower warps are
+                    // still reading for the latched frames.
+                    if (running) __syncthreads();
                 }
                 if (!running) break;
             }

@@ -52,6 +52,23 @@ class NbLdpcCode:
     def in_elems(self, in_kind):
         return {IN_SYMBOL_LLR: self.N * (self.q - 1), IN_BPSK: self.N * self.p, IN_QAM: self.N * 2}[in_kind]
 
+    def sigma(self, snrtype, snr_db, n_qam=0):
+        """main.cu:221-228 (n_qam <= 0: the loaded constellation's size)."""
+        return float(lib.nb_ldpc_sigma(self._h, int(snrtype), float(snr_db), int(n_qam)))
+
+    def modulate_awgn(self, F, sigma, *, seed=173, first_frame=0, codeword=None, stream=None):
+        """BitToSym / Modulate + complex AWGNChannel_CPU (LDPC_Encoder.cpp:6-68) on the device: returns a CUDA
+        float32 tensor [F, N*p] (BPSK) or [F, N, 2] (QAM).  codeword: CUDA int16/uint16 tensor [N] or None."""
+        import torch
+        bpsk = self.n_const == 2
+        x = torch.empty((F, self.N * self.p) if bpsk else (F, self.N, 2), dtype=torch.float32, device="cuda")
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        rc = lib.nb_ldpc_modulate_awgn(self._h, x.data_ptr(), int(F), float(sigma), int(seed), int(first_frame),
+                                       codeword.data_ptr() if codeword is not None else None, st)
+        if rc < 0:
+            raise LdpcError(rc, "nb_ldpc_modulate_awgn")
+        return x
+
     def decode(self, inp, iters=20, *, algo=ALGO_EMS, in_kind=IN_SYMBOL_LLR, sigma=1.0, ems_nm=2, ems_nc=2, stream=None):
         """inp: float32 [F, in_elems] numpy array (host path) or torch CUDA tensor (device path)."""
         per = self.in_elems(in_kind)
