@@ -96,9 +96,10 @@ def test_fresh_sum_agrees_with_literal_on_converged_frames(nb_oracle, gf_dir, me
     h = load(nb_oracle, gf_dir, cfg)
     N, q, p = 96, 64, 6
     agree = 0
+    rx_all = np.ascontiguousarray(g["rx"])  # keep the buffer alive: a temporary's .ctypes.data dangles once it is freed
     for f in range(cfg["frames"]):
         lch = np.zeros(N * (q - 1), np.float32)
-        nb_oracle.nb_orc_demodulate(h, float(g["sigma"]), np.ascontiguousarray(g["rx"][f]).ctypes.data, lch.ctypes.data)
+        nb_oracle.nb_orc_demodulate(h, float(g["sigma"]), rx_all[f].ctypes.data, lch.ctypes.data)
         out = np.zeros(N, np.int32)
         it = C.c_int(0)
         r = nb_oracle.nb_orc_decode(h, 0, 1, lch.ctypes.data, 20, 2, 2, out.ctypes.data, C.byref(it))
