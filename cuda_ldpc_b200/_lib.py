@@ -3,7 +3,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libldpc_b200.so")
+# LDPC_B200_LIB: file name of an alternative build of the SAME library next to this file (the race-hunting builds
+# libldpc_b200_stress*.so of tests/test_stress_gpu.py); never a different implementation
+lib_path = os.path.join(_HERE, os.path.basename(os.environ.get("LDPC_B200_LIB", "libldpc_b200.so")))
 
 
 class LdpcError(RuntimeError):

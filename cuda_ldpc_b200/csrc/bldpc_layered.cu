@@ -23,6 +23,7 @@
 
 #include "common.h"
 #include "philox.cuh"
+#include "stress.cuh"
 
 // Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it):
 //   LDPC_REC_PRELOAD   2  the record of a thread's next step is loaded into registers right after the edge loop
@@ -460,6 +461,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         }
 #undef LDPC_ROWS
         __syncthreads();
+        LDPC_STRESS_POINT(1);
     }
 }
 
@@ -585,6 +587,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         if (dynamic) {
             if (tid == 0) s_next = atomicAdd(p.work_counter, 1);
             __syncthreads();
+            LDPC_STRESS_POINT(6);
             g = s_next;
         }
         if (g >= p.num_groups) break;
@@ -719,6 +722,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         }
         if (tid == 0) s_fail[0] = s_fail[1] = 0u;
         __syncthreads();
+        LDPC_STRESS_POINT(5);
         // pull the channel values of this CTA's next group towards L2 while this group is decoded
         if (LDPC_L2_PREFETCH && !dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
             p.layout == LDPC_LAYOUT_NF) {
@@ -748,9 +752,11 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                     unsigned fail = 0u;
                     for (int i = tid; i < Z; i += T) fail |= syndrome_row(smem, p, off, dc, 4 * i, Z4);
                     fail = __reduce_or_sync(0xffffffffu, fail);
-                    if ((tid & 31) == 0 && fail) atomicOr(&s_fail[r & 1], fail);
+                    constexpr int kFlip = LDPC_R1_RACES ? 0 : 1;
+                    if ((tid & 31) == 0 && fail) atomicOr(&s_fail[r & kFlip], fail);
                     __syncthreads();
-                    fl |= s_fail[r & 1];                 // words accumulate over layers r, r-2, ...: OR is idempotent
+                    LDPC_STRESS_POINT(2);
+                    fl |= s_fail[r & kFlip];             // words accumulate over layers r, r-2, ...: OR is idempotent
                     if ((fl & rbytes) == rbytes) break;  // uniform: nobody writes this word before the next barrier
                 }
                 __syncthreads();  // every read of s_fail is done
@@ -760,6 +766,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                                         (((~fl) >> 28) & 8u);
                 const unsigned finish = (it == p.iters) ? running : (running & okmask);
                 if (finish) {
+                    LDPC_STRESS_POINT(3);
                     write_outputs(appw, p, g, finish);
                     if (p.dbg_rec) dump_records<DCMAX>(p, rec, g, finish);
                     if (tid < 4 && ((finish >> tid) & 1u)) {
@@ -772,12 +779,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                     // `finish` is CTA-uniform.  The frames that keep running go straight into the next sweep, which
                     // rewrites the APP words and records that write_outputs / dump_records of slower warps are
                     // still reading for the latched frames.
-                    if (running) __syncthreads();
+                    if (running && !LDPC_R1_RACES) __syncthreads();
                 }
                 if (!running) break;
             }
         }
         __syncthreads();  // everyone is done with appw before the next group's load
+        LDPC_STRESS_POINT(4);
     }
 }
 

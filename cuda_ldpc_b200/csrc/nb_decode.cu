@@ -15,8 +15,16 @@
 
 #include "common.h"
 #include "nb_common.h"
+#include "stress.cuh"
 
 namespace ldpcb {
+
+// every CTA barrier of this file; race-hunting builds (-DLDPC_STRESS=1, stress.cuh) skew the warps behind it
+__device__ __forceinline__ void cta_sync()
+{
+    __syncthreads();
+    LDPC_STRESS_POINT(0);
+}
 
 constexpr int kNbThreads = 256;      // CTA width when the frame state lives in the global scratch slot
 constexpr int kNbThreadsMax = 1024;  // ... and the widest CTA tried when it fits in shared memory
@@ -421,7 +429,7 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
     const int warp = tid >> 5, nwarps = T >> 5, lane = tid & 31;
     for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 0.0f;
     if (tid == 0) *s_fail = 0;
-    __syncthreads();
+    cta_sync();
     // output edges of a row are split over several warps when there are fewer rows than 2 x warps (C5: M = 12)
     int split = (2 * nwarps + M - 1) / M;
     split = split < 1 ? 1 : (split > p.dc_max ? p.dc_max : split);
@@ -448,11 +456,11 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
             }
 #undef VN
         }
-        __syncthreads();
+        cta_sync();
         syndrome(p, sym, s_fail);
-        __syncthreads();
+        cta_sync();
         const int fail = *s_fail;
-        __syncthreads();
+        cta_sync();
         if (tid == 0) *s_fail = 0;
         if (fail == 0) {
             ok = 1;
@@ -484,7 +492,7 @@ __device__ void decode_ems(const NbParams &p, int f, float *lch, float *LLR, flo
                 default: ems_check_row_warp<0>(p, row, d0, d1, v2c, topsym, topval, c2v, ws, lane);
             }
         }
-        __syncthreads();
+        cta_sync();
     }
     if (tid == 0) {
         if (p.iters_out) p.iters_out[f] = it;
@@ -510,7 +518,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         const int vn = p.c_vn[row * p.dc_max + d];
         s.vv[d * q + a] = __fsub_rn(LLR[vn * q + a], c2v[((size_t)row * p.dc_max + d) * q + a]);
     }
-    __syncthreads();
+    cta_sync();
     // d_TMM_Get_Zn :704-723: hard symbol of every edge = first minimum of its v2c vector.  q >= 32: one warp of
     // the group per edge (lanes scan x = lane, lane+32, ... then a warp argmin, lowest x on ties); dc may exceed q
     if (q >= 32) {
@@ -546,7 +554,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
             s.Zn[d] = me;
         }
     }
-    __syncthreads();
+    cta_sync();
     if (act && a == 0) {
         int syn = 0;
         for (int d = 0; d < w; d++) syn ^= s.Zn[d];
@@ -557,7 +565,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         const float mn = s.vv[d * q + gmul(p, hinv, s.Zn[d])];
         s.dU[d * q + (a ^ s.Zn[d])] = __fsub_rn(s.vv[d * q + gmul(p, hinv, a)], mn);
     }
-    __syncthreads();
+    cta_sync();
     if (act) {  // TMM_Get_Min :745-770
         float m1 = INFINITY, m2 = INFINITY;
         int col = 0;
@@ -575,7 +583,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         s.MinCol[a] = col;
         s.MC[a] = make_int2(__float_as_int(m1), col);
     }
-    __syncthreads();
+    cta_sync();
     if (act) {  // TMM_ConstructConf :772-817.  dU[MinCol[j]][j] IS Min1[j], so the two-deviation search reads one
                 // {Min1, MinCol} pair per symbol (a broadcast for j, a permutation for a ^ j) and selects without branches:
                 // "(d1 > d2 && d1 < I) or (d1 < d2 && d2 < I)"  ==  "d1 != d2 && max(d1, d2) < I"
@@ -610,7 +618,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         s.Path[2 * a] = p0;
         s.Path[2 * a + 1] = p1;
     }
-    __syncthreads();
+    cta_sync();
     const int syn = act ? s.Zn[p.dc_max] : 0;
     for (int d = 0; d < w; d++) {  // :496-521, thread = eta
         const float l = (a == 0) ? 0.0f : ((d != s.Path[2 * a] && d != s.Path[2 * a + 1]) ? s.I[a] : s.Ev[a]);
@@ -623,7 +631,7 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
             LLR[vn * q + beta] = __fadd_rn(s.vv[d * q + beta], m);
         }
     }
-    __syncthreads();
+    cta_sync();
 }
 
 __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, float *c2v, uint16_t *sym, float *smem,
@@ -638,7 +646,7 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
         for (int a = 1; a < q; a++) LLR[col * q + a] = __fsub_rn(mx, lch[col * (q - 1) + a - 1]);
     }
     for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 0.0f;
-    __syncthreads();
+    cta_sync();
     // thread groups of q threads: one check per group (layered: a single group keeps the row order)
     const int groups = layered ? 1 : max(1, T / q);
     const int g = tid / q, a = tid - g * q;
@@ -670,7 +678,7 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
             }
         }
         if (tid == 0) *s_fail = 0;
-        __syncthreads();
+        cta_sync();
         for (int col = tid; col < N; col += T) {  // d_DecideLLRVector :92-105 (first minimum)
             float mn = INFINITY;
             int best = 0;
@@ -681,9 +689,9 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
                 }
             sym[col] = (uint16_t)best;
         }
-        __syncthreads();
+        cta_sync();
         syndrome(p, sym, s_fail);
-        __syncthreads();
+        cta_sync();
         if (*s_fail == 0) {
             ok = 1;
             it--;
@@ -721,7 +729,7 @@ __device__ __forceinline__ void wht_stage_all(float *F, int q, int w, int a)
                 F[d * q + j + len] = __fsub_rn(u, v);
             }
         }
-        __syncthreads();
+        cta_sync();
     }
 }
 
@@ -840,7 +848,7 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
     }
     for (int i = tid; i < M * p.dc_max * q; i += T) c2v[i] = 1.0f;
     if (tid == 0) *s_fail = 0;
-    __syncthreads();
+    cta_sync();
     const int groups = max(1, T / q), g = tid / q, a = tid - g * q;
     const size_t per_group = (size_t)2 * p.dc_max * q;
     float *F = smem + (size_t)(g < groups ? g : 0) * per_group, *G = F + (size_t)p.dc_max * q;
@@ -852,11 +860,11 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
             FFT_PER(CALL)
 #undef CALL
         }
-        __syncthreads();
+        cta_sync();
         syndrome(p, sym, s_fail);
-        __syncthreads();
+        cta_sync();
         const int fail = *s_fail;
-        __syncthreads();
+        cta_sync();
         if (tid == 0) *s_fail = 0;
         if (fail == 0) {
             ok = 1;
@@ -872,7 +880,7 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
                 const float *v = v2c + ((size_t)p.c_vn[row * p.dc_max + d] * p.dv_max + p.c_pos[row * p.dc_max + d]) * q;
                 F[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])] = v[a];
             }
-            __syncthreads();
+            cta_sync();
             wht_stage_all(F, q, w, a);
             for (int d = 0; d < w; d++) {  // products of the other edges' transforms, ascending edge position
                 float gy = 1.0f;
@@ -884,22 +892,22 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
                 }
                 G[d * q + a] = gy;
             }
-            __syncthreads();
+            cta_sync();
             wht_stage_all(G, q, w, a);
             for (int d = 0; d < w; d++) {  // permute back, clamp; F is dead and takes the clamped values
                 const float gv = G[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])];
                 F[d * q + a] = gv > 1e-30f ? gv : 1e-30f;
             }
-            __syncthreads();
+            cta_sync();
             for (int d = 0; d < w; d++) G[d * q + a] = F[d * q + a];
-            __syncthreads();
+            cta_sync();
             for (int len = q / 2; len >= 1; len >>= 1) {  // tree sums of all output edges
                 if (a < len)
                     for (int d = 0; d < w; d++) G[d * q + a] = __fadd_rn(G[d * q + a], G[d * q + a + len]);
-                __syncthreads();
+                cta_sync();
             }
             for (int d = 0; d < w; d++) c2v[((size_t)row * p.dc_max + d) * q + a] = __fdiv_rn(F[d * q + a], G[d * q]);
-            __syncthreads();
+            cta_sync();
         }
     }
 #undef FFT_PER
@@ -930,7 +938,7 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
     const int q = p.q, N = p.N, M = p.M;
     if (NB_MUL_SMEM && q <= kMulSmemQ) {
         for (int i = threadIdx.x; i < q * q; i += blockDim.x) g_smul[i] = p.mul[i];
-        __syncthreads();
+        cta_sync();
     }
     const bool has_v2c = p.algo == NB_ALGO_EMS || p.algo == NB_ALGO_FFT_BP;
     float *lch = slot;
@@ -943,16 +951,16 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
     uint16_t *sym = topsym + ((ntop + 1) & ~(size_t)1);
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         demodulate(p, f, lch);
-        __syncthreads();
+        cta_sync();
         if (p.algo == NB_ALGO_EMS)
             decode_ems(p, f, lch, LLR, c2v, v2c, topval, topsym, sym, smem, &s_fail);
         else if (p.algo == NB_ALGO_FFT_BP)
             decode_fftbp(p, f, lch, LLR, c2v, v2c, sym, smem, &s_fail);
         else
             decode_tmm(p, f, lch, LLR, c2v, sym, smem, &s_fail, p.algo == NB_ALGO_LAYERED_TMM);
-        __syncthreads();
+        cta_sync();
         for (int col = threadIdx.x; col < N; col += blockDim.x) p.out[(size_t)f * N + col] = sym[col];
-        __syncthreads();
+        cta_sync();
     }
 }
 
