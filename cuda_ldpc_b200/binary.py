@@ -152,7 +152,7 @@ class LdpcCode:
             if debug:
                 if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
                     app = torch.zeros(N * F, dtype=torch.uint8, device=dev)
-                    msgs = torch.zeros(self.M * 4 * F, dtype=torch.int32, device=dev)
+                    msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.int8, device=dev)
                 elif schedule == SCHED_LAYERED:
                     app = torch.zeros(N * F, dtype=torch.float32, device=dev)
                     msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.float32, device=dev)
@@ -194,7 +194,7 @@ class LdpcCode:
         if debug:
             if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
                 app = np.zeros(N * F, np.int8)
-                msgs = np.zeros(self.M * 4 * F, np.uint32)
+                msgs = np.zeros(self.M * self.dc_max * F, np.int8)
             elif schedule == SCHED_LAYERED:
                 app = np.zeros(N * F, np.float32)
                 msgs = np.zeros(self.M * self.dc_max * F, np.float32)

@@ -277,7 +277,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
     const size_t dbg_app_bytes =
         o->debug_app ? (size_t)c->N * F * (layered_f32 ? 4 : (flooding ? 0 : 1)) : 0;
     const size_t dbg_msg_bytes =
-        o->debug_msgs ? (flooding ? (size_t)c->M * c->dc_max * F * 4 : (size_t)c->M * 4 * F * 4) : 0;
+        o->debug_msgs ? (size_t)c->M * c->dc_max * F * (flooding ? 4 : 1) : 0;  // fp32 messages / int8 c2v messages
 
     // ---- scratch carve-up (one arena per handle; decode calls on one handle serialise on it)
     size_t need = 0;

@@ -62,8 +62,9 @@ struct LayeredParams {
     void *out;
     int *iters_out, *ok_out;
     signed char *dbg_app;
-    unsigned *dbg_rec;
-    uint4 *rec;             // scratch: per CTA, M records of REC_U4 uint4
+    signed char *dbg_msg;
+    int dc_max;
+    uint4 *rec;             // scratch: per CTA, M message blocks of MsgLayout::STRIDE uint4
     int *work_counter;      // dynamic group scheduling (early exit), or nullptr
     int llr_dtype, layout, out_format;
     int F, N, Z, J, M;
@@ -85,41 +86,25 @@ struct LayeredParams {
     LayerTables lt;         // compact form, used by the debug dump only
 };
 
-// Check records: 256-bit global accesses with the L2 evict-last policy (LDG.E.ELL2.256 /
-// STG.E.ELL2.256 on sm_100a) so that the per-CTA record slices are the last thing L2 gives up while the
-// channel values stream through; the trailing 128 bits of wide records use a plain access.
-template <int U4>
-__device__ __forceinline__ void rec_load(const uint4 *p, unsigned *rw)
+// Check-to-variable messages: per check row a block of CH x 8 words, word k = the c2v bytes (message + 127) of
+// edge k for the 4 codewords of the group.  256-bit global accesses with the L2 evict-last policy
+// (LDG.E.ELL2.256 / STG.E.ELL2.256 on sm_100a) so that the per-CTA message slices are the last thing L2 gives
+// up while the channel values stream through.
+template <int CH>
+__device__ __forceinline__ void msg_load(const uint4 *p, unsigned *w)
 {
-    asm volatile("ld.global.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]), "=r"(rw[4]), "=r"(rw[5]), "=r"(rw[6]), "=r"(rw[7])
-                 : "l"(p));
-    if (U4 == 3) {
-        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(rw[8]), "=r"(rw[9]), "=r"(rw[10]), "=r"(rw[11])
-                     : "l"(p + 2));
-    } else if (U4 == 4) {
+#pragma unroll
+    for (int c = 0; c < CH; c++)
         asm volatile("ld.global.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(rw[8]), "=r"(rw[9]), "=r"(rw[10]), "=r"(rw[11]), "=r"(rw[12]), "=r"(rw[13]), "=r"(rw[14]),
-                       "=r"(rw[15])
-                     : "l"(p + 2));
-    }
+                     : "=r"(w[8 * c + 0]), "=r"(w[8 * c + 1]), "=r"(w[8 * c + 2]), "=r"(w[8 * c + 3]),
+                       "=r"(w[8 * c + 4]), "=r"(w[8 * c + 5]), "=r"(w[8 * c + 6]), "=r"(w[8 * c + 7])
+                     : "l"(p + 2 * c));
 }
-template <int U4>
-__device__ __forceinline__ void rec_store(uint4 *p, const unsigned *rw)
+__device__ __forceinline__ void msg_store8(uint4 *p, const unsigned *w)
 {
-    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(rw[0]), "r"(rw[1]),
-                 "r"(rw[2]), "r"(rw[3]), "r"(rw[4]), "r"(rw[5]), "r"(rw[6]), "r"(rw[7])
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
-    if (U4 == 3) {
-        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p + 2), "r"(rw[8]), "r"(rw[9]), "r"(rw[10]),
-                     "r"(rw[11])
-                     : "memory");
-    } else if (U4 == 4) {
-        asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p + 2), "r"(rw[8]),
-                     "r"(rw[9]), "r"(rw[10]), "r"(rw[11]), "r"(rw[12]), "r"(rw[13]), "r"(rw[14]), "r"(rw[15])
-                     : "memory");
-    }
 }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -160,288 +145,195 @@ __device__ __forceinline__ __half2 beta_scale(__half2 m, __half2 mul, __half2 nb
     return __hsub2(m, fl);
 }
 
-// Sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)), 10 edges per accumulator so the
-// value stays below 1024 and its bit pattern can be read off 1024 + acc.  Edge k of a degree-dc
-// check lives in sign word g = k/10 at bit (min(10, dc-10g) - 1 - (k-10g)) of each 16-bit lane.
-constexpr int kSignGroup = 10;
-template <int DCMAX>
-struct RecLayout {
-    static constexpr int SW = (DCMAX + kSignGroup - 1) / kSignGroup;  // sign words per half-group
-    static constexpr int WORDS = 6 + 2 * SW;                          // m1 x2, m2 x2, idx x2, signs
-    static constexpr int U4 = (WORDS + 3) / 4;                        // uint4 moved per record (2..4)
-    static constexpr int STRIDE = U4 <= 2 ? 2 : 4;  // uint4 between records: every record 32-byte aligned
-};
-__host__ __device__ constexpr int sign_bit_pos(int dc, int k)
-{
-    const int g = k / kSignGroup, j = k - g * kSignGroup;
-    const int gs = (dc - g * kSignGroup) < kSignGroup ? (dc - g * kSignGroup) : kSignGroup;
-    return gs - 1 - j;
-}
-
-// One check row of one layer for the 4 codewords of the group.
-// EXACT: the check degree is the template constant DC (no per-edge branches, every table entry is
-// a constant-bank load at an immediate offset, every shift amount is an immediate).  !EXACT: DC is
-// the bucket's maximum and edges k >= dc are predicated off (rare degrees only).
-//
-// Number formats (all exact):
-//  * smem byte b = APP + 127 (0..254).  PRMT with the constant byte 0x65 turns it into the fp16 pattern
-//    0x6500|b = 1280 + b = APP + 1407; t' = t + 1407 then stays inside the binade [1024, 2048) for every
-//    reachable t (|t| <= 254) and so does t' + c2v_new, where an fp16 pattern is 0x6400 + (value - 1024):
-//    the final "add, clamp to [-127,127], re-bias" is ONE integer SIMD instruction on the pattern,
-//    VIADDMNMX.S16x2.RELU: max(min(pattern - 0x6500, 254), 0) = clamp(APP_new) + 127.
-//  * min1 / min2 / first index are tracked on keys |t|*8 + (k mod 8) (< 2048, exact in fp16; positive
-//    fp16 patterns order like unsigned integers, so VIMNMX(3).U16x2 does the comparisons), one
-//    accumulator pair per set of 8 edges; the amax clamp commutes with the minimum and is applied to
-//    the keys once per row (key1 -> min(key1, 8*amax) also yields the oracle's "first index" when every
-//    |t| saturates).  Keys are decoded (floor(key/8), key mod 8) on the FMA pipe.
-//  * sign bits are collected on the fp16 pipe (acc = 2*acc + (t<0)); (t<0) is an HSET2 (LDPC_NEG_ALU) or fma.sat(t, -1, 0).
-// Pipe balance (profiles/r01_pipe_ubench.txt: every instruction here issues once per 2 cycles per sub-partition,
-// HFMA2 / HADD2 / IMAD on one pipe, HSET2 / VIMNMX / LOP3 / PRMT on the other, ~0.8 IPC at best when mixed): per
-// edge and pair of frames the ALU pipe sees PRMT, HSET2.EQ, LOP3, HSET2.LT, 2.5 x VIMNMX, 0.5 x LOP3 (parity) in
-// phase 1 and HSET2.EQ, LOP3, VIADDMNMX in phase 2; the FMA pipe the select HFMA2, IMAD.SHL, two HADD2, the sign
-// and key HFMA2 in phase 1 and HFMA2, IMAD.SHL, HADD2 in phase 2, plus decode / beta scaling per row.  A/B runs
-//  put the optimum at this split: moving one more op either way loses.
-__device__ __forceinline__ __half2 neg01(__half2 t)
-{
-    unsigned d;
-    asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(h2u(t)), "r"(0xBC00BC00u), "r"(0u));
-    return u2h(d);
-}
 __device__ __forceinline__ __half2 umin2(__half2 a, __half2 b) { return u2h(__vminu2(h2u(a), h2u(b))); }
 __device__ __forceinline__ __half2 umax2(__half2 a, __half2 b) { return u2h(__vmaxu2(h2u(a), h2u(b))); }
 __device__ __forceinline__ __half2 umin3(__half2 a, __half2 b, __half2 c)
 {
     return u2h(__vimin3_u16x2(h2u(a), h2u(b), h2u(c)));
 }
-// floor(c / 8) for integer-valued 0 <= c <= 1023: c/8 - 7/16 has at most 11 significant bits, and adding
-// 1025 (ulp 1, never a tie) rounds it to 1025 + floor
-__device__ __forceinline__ __half2 floor8(__half2 c)
-{
-    const __half2 k = __float2half2_rn(1025.0f);
-    const __half2 u = __hfma2(c, __float2half2_rn(0.125f), __float2half2_rn(-0.4375f));
-    return __hsub2(__hadd2(u, k), k);
-}
 
-// Record flow: `rw` holds this row's record on entry (!FIRST) and the record of the thread's NEXT step on
-// exit (`ld_next`: the load is issued between the two phases, so its latency hides under phase 2; the
-// registers of the old record are dead by then).
+// Message block of a check row in the kernel's degree bucket
+template <int DCMAX>
+struct MsgLayout {
+    static constexpr int CH = (DCMAX + 7) / 8;  // 256-bit chunks per row
+    static constexpr int WORDS = CH * 8;
+    static constexpr int STRIDE = CH * 2;        // uint4 between rows: every row 32-byte aligned
+};
+
+// One check row of one layer for the 4 codewords of the group.
+// EXACT: the check degree is the template constant DC (no per-edge branches, every table entry is
+// a constant-bank load at an immediate offset).  !EXACT: DC is the bucket's maximum and edges k >= dc are
+// predicated off (rare degrees only).
+//
+// Number formats (all exact):
+//  * smem byte b = APP + 127 (0..254) and message byte c = c2v + 127.  PRMT with the constant byte 0x65 turns a
+//    byte into the fp16 pattern 0x6500|b = 1280 + b = value + 1407, so t = APP - c2v_old is ONE HADD2 of the two
+//    patterns (the biases cancel), two frames per instruction.
+//  * min1 / min2 are tracked on the patterns of |t| with VIMNMX(3).U16x2 (positive fp16 patterns order like
+//    unsigned integers): 2.5 min/max per edge; the amax clamp commutes with the minimum and is applied once per row.
+//  * The oracle's "k == first index of the minimum" needs no index at all for the NEW message: |t_k| <= min1 holds
+//    for the first minimum and otherwise only when min2 == min1, where both choices give the same value.  The
+//    select is fma.sat(|t_k|, -1, min1 + 1) in {0, 1} on the FMA pipe, then mag = sel * (m2' - m1') + m1'.
+//  * sign of the new message = parity ^ sign(t_k): parity = xor of the t patterns (bit 15 of a lane); +-1.0 with
+//    that sign is one LOP3, the signed biased message nb = mag * (+-1) + 1407 one HFMA2, nb + t = APP_new + 1407
+//    stays inside the binade [1024, 2048) where the pattern is 0x6400 + (value - 1024): "clamp to [-127, 127],
+//    re-bias" is ONE integer SIMD instruction, VIADDMNMX.S16x2.RELU: max(min(pattern - 0x6500, 254), 0).
+//    The low byte of nb's pattern IS the message byte to store.
+// Round 1 kept compressed records {min1, min2, idx, sign bits} per check instead (same bytes for dc = 8, fewer for
+// dc >= 12) and rebuilt the old message of every edge from them: 5 more instructions per edge and pair of frames
+// in phase 1, plus sign collection and index tracking (keyed minima, decode) — 57 instead of ~42 instructions per
+// edge and 4 codewords.
+//
+// Message flow: `mw` holds this row's old messages on entry (!FIRST) and those of the thread's NEXT step on exit
+// (`ld_next`: the load is issued between the two phases, so its latency hides under phase 2).
 template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const LayeredParams &p, int off, int dc_rt,
-                                              int Z4, uint4 *recp, const uint4 *nx, bool ld_next,
-                                              unsigned (&rw)[RecLayout<DCHI>::U4 * 4], __half2 amax8,
-                                              __half2 amax8p7, __half2 bmul, __half2 nbias)
+                                              int Z4, uint4 *msgp, const uint4 *nx, bool ld_next,
+                                              unsigned (&mw)[MsgLayout<DCHI>::WORDS], __half2 amaxp, __half2 bmul,
+                                              __half2 nbias)
 {
-    constexpr int SW = RecLayout<DCHI>::SW;  // record layout of the kernel's degree bucket
-    constexpr int U4 = RecLayout<DCHI>::U4;
-    constexpr int NS = (DC + 7) / 8;         // key sets
+    constexpr int CH = MsgLayout<DCHI>::CH;
     const int dc = EXACT ? DC : dc_rt;
-    if (!FIRST && !LDPC_REC_PRELOAD) rec_load<U4>(recp, rw);
-    // record words: [0,1] m1 (frames 01, 23)  [2,3] m2  [4,5] idx  [6 + h*SW + g] sign words
-    const __half2 kbias = __float2half2_rn(1407.0f), k1024 = __float2half2_rn(1024.0f);
-    const __half2 zero = __float2half2_rn(0.0f), two = __float2half2_rn(2.0f), eight = __float2half2_rn(8.0f);
+    const __half2 kbias = __float2half2_rn(1407.0f), one = __float2half2_rn(1.0f);
     const __half2 sent = __float2half2_rn(2047.0f);
-    __half2 dold[2];
-    if (!FIRST) {
-        dold[0] = __hsub2(u2h(rw[2]), u2h(rw[0]));
-        dold[1] = __hsub2(u2h(rw[3]), u2h(rw[1]));
-    }
     unsigned addr[DC];
-    __half2 tp[2][DC];
-    __half2 k1[2][NS], k2[2][NS], kprev[2];
-    __half2 cnt[2] = {zero, zero};  // !LDPC_PARITY_XOR: number of negative t per lane
-    unsigned par[2] = {0u, 0u};     // LDPC_PARITY_XOR: xor of the t patterns, bit 15 of a lane = sign parity
-    __half2 sacc[2][SW];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-#pragma unroll
-        for (int g = 0; g < SW; g++) sacc[h][g] = zero;
-#pragma unroll
-        for (int s = 0; s < NS; s++) k1[h][s] = k2[h][s] = sent;
-    }
+    __half2 tt[2][DC];
+    __half2 k1[2] = {sent, sent}, k2[2] = {sent, sent}, kprev[2];
+    unsigned par[2] = {0u, 0u};  // xor of the t patterns, bit 15 of a lane = sign parity
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
-            const int s = k >> 3, kl = k & 7;
-            const __half2 kh = __float2half2_rn((float)k), klh = __float2half2_rn((float)kl);
             const int2 e = p.tab[off + k];  // {column-block base + shift (bytes), wrap threshold (Z - s) * 4}
             unsigned a = isb + (unsigned)e.x;
             a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
             addr[k] = a;
             const unsigned wk = lds32(a);
-            const int sh = 15 - sign_bit_pos(dc, k);  // brings edge k's sign bit to bit 15 of each lane
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                __half2 t1 = u2h(prmt(wk, p.c65, h ? 0x4342u : 0x4140u));
-                if (!FIRST) {
-                    const __half2 mag = __hfma2(__heq2(u2h(rw[4 + h]), kh), dold[h], u2h(rw[h]));
-                    const unsigned sg = (rw[6 + h * SW + k / kSignGroup] << sh) & 0x80008000u;
-                    t1 = __hsub2(t1, u2h(h2u(mag) ^ sg));
-                }
-                tp[h][k] = t1;
-                const __half2 tt = __hsub2(t1, kbias);
-                const __half2 neg = LDPC_NEG_ALU ? __hlt2(tt, zero) : neg01(tt);  // 1.0 where t < 0
-                sacc[h][k / kSignGroup] = __hfma2(sacc[h][k / kSignGroup], two, neg);
-                if (LDPC_PARITY_XOR)
-                    par[h] ^= h2u(tt);
-                else
-                    cnt[h] = __hadd2(cnt[h], neg);
-                const __half2 key = __hfma2(__habs2(tt), eight, klh);
+                const __half2 ap = u2h(prmt(wk, p.c65, h ? 0x4342u : 0x4140u));
+                const __half2 t = FIRST ? __hsub2(ap, kbias) : __hsub2(ap, u2h(prmt(mw[k], p.c65, h ? 0x4342u : 0x4140u)));
+                tt[h][k] = t;
+                par[h] ^= h2u(t);
+                const __half2 av = __habs2(t);
                 if (!EXACT) {
-                    k2[h][s] = umin2(k2[h][s], umax2(k1[h][s], key));
-                    k1[h][s] = umin2(k1[h][s], key);
-                } else if ((kl & 1) == 0) {
+                    k2[h] = umin2(k2[h], umax2(k1[h], av));
+                    k1[h] = umin2(k1[h], av);
+                } else if ((k & 1) == 0) {
                     if (k == DC - 1) {  // unpaired last edge
-                        k2[h][s] = umin2(k2[h][s], umax2(k1[h][s], key));
-                        k1[h][s] = umin2(k1[h][s], key);
+                        k2[h] = umin2(k2[h], umax2(k1[h], av));
+                        k1[h] = umin2(k1[h], av);
                     } else {
-                        kprev[h] = key;
+                        kprev[h] = av;
                     }
-                } else {  // pair (k-1, k): 5 min/max for two edges, 2 for the first pair of a set
-                    const __half2 lo = umin2(kprev[h], key), hi = umax2(kprev[h], key);
-                    if (kl == 1) {
-                        k1[h][s] = lo;
-                        k2[h][s] = hi;
+                } else {  // pair (k-1, k): 5 min/max for two edges, 2 for the first pair
+                    const __half2 lo = umin2(kprev[h], av), hi = umax2(kprev[h], av);
+                    if (k == 1) {
+                        k1[h] = lo;
+                        k2[h] = hi;
                     } else {
-                        k2[h][s] = umin3(k2[h][s], hi, umax2(k1[h][s], lo));
-                        k1[h][s] = umin2(k1[h][s], lo);
+                        k2[h] = umin3(k2[h], hi, umax2(k1[h], lo));
+                        k1[h] = umin2(k1[h], lo);
                     }
                 }
             }
         }
     }
-    // the old record is dead: start the load of the next step's record, ~150 instructions of row finalisation
-    // and the whole phase 2 before its first use
-    if (LDPC_REC_PRELOAD == 2 && ld_next) rec_load<U4>(nx, rw);
-    unsigned nsg[2][SW], rwn[U4 * 4];
-#pragma unroll
-    for (int w = 6 + 2 * SW; w < U4 * 4; w++) rwn[w] = 0u;  // padding words of the record
-    __half2 min1[2], idx[2], dnew[2];
+    // the old messages are dead: start the load of the next step's block, the row finalisation and the whole
+    // phase 2 before its first use
+    if (ld_next) msg_load<CH>(nx, mw);
+    __half2 min1[2], dnew[2], m1p1[2];
+    unsigned pm1[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        __half2 m1 = zero, m2 = zero, ix = zero;
-#pragma unroll
-        for (int s = 0; s < NS; s++) {
-            const __half2 c1 = umin2(k1[h][s], amax8), c2 = umin2(k2[h][s], amax8p7);
-            const __half2 a1 = floor8(c1), a2 = floor8(c2);
-            const __half2 ia = __hfma2(a1, __float2half2_rn(-8.0f), c1);
-            if (s == 0) {
-                m1 = a1;
-                m2 = a2;
-                ix = ia;
-            } else {  // strict "<": the earlier set keeps the index on equal minima (first index)
-                const __half2 lt = __hlt2(a1, m1);
-                ix = __hfma2(lt, __hsub2(__hadd2(ia, __float2half2_rn(8.0f * s)), ix), ix);
-                m2 = umin2(umax2(m1, a1), umin2(m2, a2));
-                m1 = umin2(m1, a1);
-            }
-        }
+        __half2 m1 = umin2(k1[h], amaxp), m2 = umin2(k2[h], amaxp);  // dc == 1: k2 is the sentinel -> amax
+        m1p1[h] = __hadd2(m1, one);
         if (p.scale_on) {
             m1 = beta_scale(m1, bmul, nbias);
             m2 = beta_scale(m2, bmul, nbias);
         }
         min1[h] = m1;
-        idx[h] = ix;
         dnew[h] = __hsub2(m2, m1);
-        // parity of the negative-sign count -> 0xFFFF per lane; sign bits of all dc edges flip with it
-        const unsigned pm = LDPC_PARITY_XOR ? ((par[h] >> 15) & 0x00010001u) * 0xFFFFu
-                                            : (h2u(__hadd2(cnt[h], k1024)) & 0x00010001u) * 0xFFFFu;
-#pragma unroll
-        for (int g = 0; g < SW; g++) {
-            int gs = dc - g * kSignGroup;
-            gs = gs < 0 ? 0 : (gs > kSignGroup ? kSignGroup : gs);
-            const unsigned gm = ((1u << gs) - 1u) * 0x00010001u;
-            nsg[h][g] = (h2u(__hadd2(sacc[h][g], k1024)) ^ pm) & gm;
-        }
-        rwn[h] = h2u(m1);
-        rwn[2 + h] = h2u(m2);
-        rwn[4 + h] = h2u(ix);
-#pragma unroll
-        for (int g = 0; g < SW; g++) rwn[6 + h * SW + g] = nsg[h][g];
+        pm1[h] = (par[h] & 0x80008000u) ^ 0x3C003C00u;  // +-1.0 carrying the parity of the negative signs
     }
-    rec_store<U4>(recp, rwn);
-    if (LDPC_REC_PRELOAD == 1 && ld_next) rec_load<U4>(nx, rw);
-
+    unsigned mn[8];
 #pragma unroll
-    for (int k = 0; k < DC; k++) {
-        if (EXACT || k < dc) {
-            const __half2 kh = __float2half2_rn((float)k);
-            const int sh = 15 - sign_bit_pos(dc, k);
-            unsigned v[2];
+    for (int k = 0; k < CH * 8; k++) {
+        if (k < DC && (EXACT || k < dc)) {
+            unsigned v[2], nbw[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const __half2 mag = __hfma2(__heq2(idx[h], kh), dnew[h], min1[h]);
-                const unsigned sg = (nsg[h][k / kSignGroup] << sh) & 0x80008000u;
-                const __half2 x = __hadd2(tp[h][k], u2h(h2u(mag) ^ sg));
+                const __half2 t = tt[h][k];
+                unsigned sl;  // 1.0 where |t| <= min1 (this edge holds the minimum), else 0
+                asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(sl) : "r"(h2u(__habs2(t))), "r"(0xBC00BC00u), "r"(h2u(m1p1[h])));
+                const __half2 mag = __hfma2(u2h(sl), dnew[h], min1[h]);
+                const unsigned sg = (h2u(t) & 0x80008000u) ^ pm1[h];
+                const __half2 nb = __hfma2(mag, u2h(sg), kbias);
+                const __half2 x = __hadd2(nb, t);
                 // pattern(x) = 0x6400 + (APP_new + 383): subtract 0x6500, clamp to [0, 254]
                 v[h] = __viaddmin_s16x2_relu(h2u(x), 0x9B009B00u, 0x00FE00FEu);
+                nbw[h] = h2u(nb);
             }
             sts32(addr[k], prmt(v[0], v[1], 0x6420u));
+            mn[k & 7] = prmt(nbw[0], nbw[1], 0x6420u);
+        } else {
+            mn[k & 7] = 0x7F7F7F7Fu;  // padding / absent edges: message 0
         }
+        if ((k & 7) == 7) msg_store8(msgp + 2 * (k >> 3), mn);
     }
 }
 
-// Address of the record a thread needs in its NEXT step (its next row of this layer, else its first row of
-// the next layer / next iteration) and whether that step reads a record at all; optional L1/L2 prefetch of
-// it (LDPC_REC_PREFETCH).  History: prefetching a whole layer ahead into L1 (80 KB in flight for
-// J15_L30_Z1280 against ~64 KB of L1) lost most lines before their use — ncu showed 26 % of the stall
-// samples as long-scoreboard waits on the record load; one step ahead was better, the register preload
-// (process_row_x) better still.
+// Address of the message block a thread needs in its NEXT step (its next row of this layer, else its first row
+// of the next layer / next iteration) and whether that step reads old messages at all.  History (round 1, compressed
+// records): prefetching a whole layer ahead into L1 (80 KB in flight for J15_L30_Z1280 against ~64 KB of L1) lost most
+// lines before their use — ncu showed 26 % of the stall samples as long-scoreboard waits on the load; one step
+// ahead was better, the register preload (process_row_x) better still; an L1 / L2 prefetch on top of it loses 2 %.
 template <int DCHI, bool FIRST>
-__device__ __forceinline__ bool prefetch_next_record(const uint4 *recl, const uint4 *nxl, int i, int T, int Z,
-                                                     bool pf_next_layer, const uint4 *&nx)
+__device__ __forceinline__ bool next_block(const uint4 *msgl, const uint4 *nxl, int i, int T, int Z, bool next_layer_reads,
+                                           const uint4 *&nx)
 {
-    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    constexpr int RS = MsgLayout<DCHI>::STRIDE;
     const bool same_layer = i + T < Z;
-    nx = same_layer ? recl + (size_t)(i + T) * RS : nxl + (size_t)threadIdx.x * RS;
-    const bool want = same_layer ? !FIRST : pf_next_layer;
-    if (LDPC_REC_PREFETCH == 1 && want) {
-        prefetch_l1(nx);
-        if (RecLayout<DCHI>::U4 > 2) prefetch_l1(nx + 2);
-    }
-    if (LDPC_REC_PREFETCH == 2 && want) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-    return want;
+    nx = same_layer ? msgl + (size_t)(i + T) * RS : nxl + (size_t)threadIdx.x * RS;
+    return same_layer ? !FIRST : next_layer_reads;
 }
 
 // Rows of a layer whose degree is outside the exact range of the kernel's bucket.  Out of line so
 // that its register needs do not leak into the allocation of the hot exact-degree paths.
 template <int DCHI, bool FIRST>
-__device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *recl,
-                                          const uint4 *nxl, bool pf_next_layer, __half2 amax8, __half2 amax8p7,
-                                          __half2 bmul, __half2 nbias)
+__device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *msgl,
+                                          __half2 amaxp, __half2 bmul, __half2 nbias)
 {
-    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    constexpr int RS = MsgLayout<DCHI>::STRIDE;
     const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
     for (int i = threadIdx.x; i < Z; i += T) {
-        const uint4 *nx;
-        prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer, nx);
-        unsigned rw[RecLayout<DCHI>::U4 * 4];  // out of line: this path loads its record itself
-        if (!FIRST && LDPC_REC_PRELOAD) rec_load<RecLayout<DCHI>::U4>(recl + (size_t)i * RS, rw);
-        process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RS, nx, false,
-                                                rw, amax8, amax8p7, bmul, nbias);
+        unsigned mw[MsgLayout<DCHI>::WORDS];  // out of line: this path loads its messages itself
+        if (!FIRST) msg_load<MsgLayout<DCHI>::CH>(msgl + (size_t)i * RS, mw);
+        process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, msgl + (size_t)i * RS, nullptr,
+                                                false, mw, amaxp, bmul, nbias);
     }
 }
 
 // One full iteration: all layers in order, the Z rows of a layer spread over the CTA.
 template <int DCHI, bool FIRST>
-__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *rec, bool last,
-                                             unsigned (&rw)[RecLayout<DCHI>::U4 * 4], __half2 amax8,
-                                             __half2 amax8p7, __half2 bmul, __half2 nbias)
+__device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *msgs, bool last,
+                                             unsigned (&mw)[MsgLayout<DCHI>::WORDS], __half2 amaxp, __half2 bmul,
+                                             __half2 nbias)
 {
-    constexpr int RS = RecLayout<DCHI>::STRIDE;
+    constexpr int RS = MsgLayout<DCHI>::STRIDE;
     const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
     for (int r = 0; r < p.J; r++) {
         const int dc = p.dc[r], off = p.off[r];
-        uint4 *recl = rec + (size_t)r * Z * RS;
+        uint4 *msgl = msgs + (size_t)r * Z * RS;
         // this thread's first row of the next layer (of the next iteration after the last layer); it is
-        // prefetched only if a sweep that reads records follows
-        const uint4 *nxl = rec + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
-        const bool pf_next_layer = (!FIRST || r == p.J - 1) && !(last && r == p.J - 1);
+        // preloaded only if a sweep that reads messages follows
+        const uint4 *nxl = msgs + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
+        const bool next_layer_reads = (!FIRST || r == p.J - 1) && !(last && r == p.J - 1);
 #define LDPC_ROWS(DCX)                                                                                        \
     for (int i = tid; i < Z; i += T) {                                                                        \
         const uint4 *nx;                                                                                      \
-        const bool ldn = prefetch_next_record<DCHI, FIRST>(recl, nxl, i, T, Z, pf_next_layer, nx);            \
-        process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * RS, nx, ldn, \
-                                              rw, amax8, amax8p7, bmul, nbias);                               \
+        const bool ldn = next_block<DCHI, FIRST>(msgl, nxl, i, T, Z, next_layer_reads, nx);                   \
+        process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, msgl + (size_t)i * RS, nx, ldn, \
+                                              mw, amaxp, bmul, nbias);                                        \
     }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
@@ -456,8 +348,8 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         } else if (DCHI >= 6 && dc == DCHI - 5) {  // (J20 / J40 / J48_L60_Z160 ran 2x slower through the generic one)
             LDPC_ROWS((DCHI >= 6 ? DCHI - 5 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
-            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, nxl, pf_next_layer, amax8, amax8p7, bmul, nbias);
-            if (LDPC_REC_PRELOAD && pf_next_layer && tid < Z) rec_load<RecLayout<DCHI>::U4>(nxl + (size_t)tid * RS, rw);
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, msgl, amaxp, bmul, nbias);
+            if (next_layer_reads && tid < Z) msg_load<MsgLayout<DCHI>::CH>(nxl + (size_t)tid * RS, mw);
         }
 #undef LDPC_ROWS
         __syncthreads();
@@ -524,29 +416,20 @@ __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int 
     }
 }
 
+// debug: the c2v messages of frames selected by `fmask` -> int8 [M][dc_max][F] (0 for absent edges)
 template <int DCMAX>
-__device__ void dump_records(const LayeredParams &p, const uint4 *rec, int g, unsigned fmask)
+__device__ void dump_messages(const LayeredParams &p, const uint4 *msgs, int g, unsigned fmask, int dc_max)
 {
-    constexpr int SW = RecLayout<DCMAX>::SW;
-    constexpr int RS = RecLayout<DCMAX>::STRIDE;
-    const unsigned *rw = reinterpret_cast<const unsigned *>(rec);
+    constexpr int RS = MsgLayout<DCMAX>::STRIDE;
+    const unsigned *mw = reinterpret_cast<const unsigned *>(msgs);
     for (int m = threadIdx.x; m < p.M; m += blockDim.x) {
-        const unsigned *r = rw + (size_t)m * RS * 4;
+        const unsigned *r = mw + (size_t)m * RS * 4;
         const int dc = p.dc[m / p.Z];
-        for (int j = 0; j < 4; j++) {
-            if (!((fmask >> j) & 1u)) continue;
-            const int h = j >> 1, sh = (j & 1) * 16;
-            const __half m1 = __ushort_as_half((unsigned short)(r[h] >> sh));
-            const __half m2 = __ushort_as_half((unsigned short)(r[2 + h] >> sh));
-            const __half ix = __ushort_as_half((unsigned short)(r[4 + h] >> sh));
-            unsigned sg = 0;
-            for (int k = 0; k < dc; k++)
-                sg |= ((r[6 + h * SW + k / kSignGroup] >> (sh + sign_bit_pos(dc, k))) & 1u) << k;
-            const size_t f = (size_t)4 * g + j;
-            p.dbg_rec[((size_t)m * 4 + 0) * p.F + f] = (unsigned)__half2int_rn(m1);
-            p.dbg_rec[((size_t)m * 4 + 1) * p.F + f] = (unsigned)__half2int_rn(m2);
-            p.dbg_rec[((size_t)m * 4 + 2) * p.F + f] = (unsigned)__half2int_rn(ix);
-            p.dbg_rec[((size_t)m * 4 + 3) * p.F + f] = sg;
+        for (int k = 0; k < dc_max; k++) {
+            const unsigned w = (k < dc) ? r[k] : 0x7F7F7F7Fu;
+            for (int j = 0; j < 4; j++)
+                if ((fmask >> j) & 1u)
+                    p.dbg_msg[((size_t)m * dc_max + k) * p.F + 4 * g + j] = (signed char)((int)((w >> (8 * j)) & 255u) - 127);
         }
     }
 }
@@ -571,9 +454,8 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     const int tid = threadIdx.x, T = blockDim.x;
     const int N = p.N, Z = p.Z, F = p.F, Z4 = 4 * Z;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-    uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * RecLayout<DCMAX>::STRIDE;
-    const __half2 amax8 = __float2half2_rn(8.0f * p.msg_max);  // key clamps: min1 -> 8*amax, min2 -> 8*amax + 7
-    const __half2 amax8p7 = __float2half2_rn(8.0f * p.msg_max + 7.0f);
+    uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * MsgLayout<DCMAX>::STRIDE;
+    const __half2 amaxp = __float2half2_rn(p.msg_max);  // magnitude clip of min1 / min2
     const __half2 bmul = __float2half2_rn(p.beta_mul);
     const __half2 nbias = __float2half2_rn(-p.beta_bias);
 
@@ -732,13 +614,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 
         unsigned running = valid;  // frames not yet latched
         int it = 0;
-        unsigned rw[RecLayout<DCMAX>::U4 * 4];  // the record of the thread's next step (LDPC_REC_PRELOAD)
+        unsigned rw[MsgLayout<DCMAX>::WORDS];  // the old messages of the thread's next step
         while (it < p.iters) {
             it++;
             if (it == 1)
-                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias);
             else
-                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amax8, amax8p7, bmul, nbias);
+                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 // The pass stops after the first layer that leaves every running frame with a failed check (the
                 // usual case until the last iterations: one layer of J is read instead of all) — the outcome
@@ -768,7 +650,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 if (finish) {
                     LDPC_STRESS_POINT(3);
                     write_outputs(appw, p, g, finish);
-                    if (p.dbg_rec) dump_records<DCMAX>(p, rec, g, finish);
+                    if (p.dbg_msg) dump_messages<DCMAX>(p, rec, g, finish, p.dc_max);
                     if (tid < 4 && ((finish >> tid) & 1u)) {
                         if (p.iters_out) p.iters_out[f0 + tid] = it;
                         if (p.ok_out) p.ok_out[f0 + tid] = (okmask >> tid) & 1u;
@@ -823,7 +705,7 @@ static int plan_i8(const ldpc_code *c, int F, I8Plan *pl)
     pl->dcb = (c->dc_max + 3) & ~3;
     int cap = 0, occ = 0, rc = LDPC_ERR_UNSUPPORTED;
     switch (pl->dcb) {
-#define X(D) case D: cap = ThreadCap<D>::value; pl->u4 = RecLayout<D>::STRIDE; break;
+#define X(D) case D: cap = ThreadCap<D>::value; pl->u4 = MsgLayout<D>::STRIDE; break;
         LDPC_BUCKETS(X)
 #undef X
         default: return LDPC_ERR_UNSUPPORTED;
@@ -871,7 +753,8 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.iters_out = a.iters_out;
     p.ok_out = a.ok_out;
     p.dbg_app = reinterpret_cast<signed char *>(a.dbg_app);
-    p.dbg_rec = reinterpret_cast<unsigned *>(a.dbg_rec);
+    p.dbg_msg = reinterpret_cast<signed char *>(a.dbg_rec);
+    p.dc_max = c->dc_max;
     p.rec = reinterpret_cast<uint4 *>(a.scratch);
     if (a.exit_mode == LDPC_EXIT_SYNDROME) {
         p.work_counter = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(a.scratch) + rec_bytes);

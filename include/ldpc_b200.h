@@ -105,7 +105,8 @@ typedef struct {
     int *ok_out;       /* [F] 1 = syndrome satisfied (genie mode: all-zero info bits), or NULL      */
     void *stream;      /* cudaStream_t, NULL = default stream                                       */
     void *debug_app;   /* optional device/host buffer receiving the final APP (layered) — tests     */
-    void *debug_msgs;  /* optional buffer receiving final messages / check records — tests          */
+    void *debug_msgs;  /* optional buffer receiving the final check-to-variable messages [M][dc_max][F] (fp32 modes:
+                          float, the reference's Memory_RQ slots; layered int8: int8, 0 for absent edges) — tests */
     /* fused channel (llr_dtype == LDPC_DTYPE_CHANNEL): y = 1 - 2c + sigma*N(0,1), Philox keyed by
      * (channel_seed, channel_first_frame + f, bit/4) exactly like ldpc_awgn_bpsk                    */
     float channel_sigma;

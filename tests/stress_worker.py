@@ -49,6 +49,8 @@ def binary(fname, geo, F, snr, iters, reps):
     assert orc.orc_layered_i8(oc.J, oc.L, oc.Z, ip(oc.H), fp(y), F, iters, 8.0, 31, 1, 3, 2, ip(D), ip(its),
                               app.ctypes.data, rec.ctypes.data) == 0
     D = D.reshape(N + 1, F)
+    from test_binary_gpu import expand_messages
+    msgs = expand_messages(rec, oc, F)
     assert its.min() < its.max()
     yd = torch.as_tensor(y, device="cuda")
     kw = dict(schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, msg_max=31, beta_num=1, beta_shift=3)
@@ -58,7 +60,7 @@ def binary(fname, geo, F, snr, iters, reps):
         check((r.D.cpu().numpy() == D).all(), f"{fname} device rep {rep}: hard bits / flags")
         check((r.iters.cpu().numpy() == its).all(), f"{fname} device rep {rep}: iterations")
         check((r.app.cpu().numpy() == app.reshape(N, F)).all(), f"{fname} device rep {rep}: APP")
-        check((r.msgs.cpu().numpy().view(np.uint32) == rec).all(), f"{fname} device rep {rep}: check records")
+        check((r.msgs.cpu().numpy() == msgs).all(), f"{fname} device rep {rep}: c2v messages")
         rh = code.decode(y, iters, out_format=m.OUT_U8, **kw)
         check((rh.D == D[:N]).all() and (rh.iters == its).all() and (rh.ok == D[N]).all(), f"{fname} host rep {rep}")
     print(f"{fname}: {reps} repeats x {F} frames, iterations {its.min()}..{its.max()}", flush=True)

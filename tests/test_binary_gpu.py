@@ -55,7 +55,21 @@ def orc_i8(oracle, oc, y, maxit, mode, scale=8.0, amax=127, bnum=0, bshift=0):
     rc = oracle.orc_layered_i8(oc.J, oc.L, oc.Z, ip(oc.H), fp(np.ascontiguousarray(y)), F, maxit, scale, amax, bnum,
                                bshift, mode, ip(D), ip(it), app.ctypes.data, rec.ctypes.data)
     assert rc == 0
-    return D.reshape(N + 1, F), it, app.reshape(N, F), rec
+    return D.reshape(N + 1, F), it, app.reshape(N, F), expand_messages(rec, oc, F)
+
+
+def expand_messages(rec, oc, F):
+    """The oracle keeps one record {min1, min2, idx, sign bits} per check; the message of edge k is
+    (sign bit k ? -1 : +1) * (k == idx ? min2 : min1).  Returns int8 [M * dc_max * F] in the layout of
+    ldpc_decode_opts_t.debug_msgs (0 for absent edges)."""
+    M, dcm = oc.M, int(oc.Wc[oc.J])
+    r = rec.reshape(M, 4, F).astype(np.int64)
+    dc_row = np.repeat((oc.H.reshape(oc.J, oc.L) >= 0).sum(1), oc.Z)          # [M]
+    k = np.arange(dcm)[None, :, None]
+    mag = np.where(k == r[:, 2][:, None, :], r[:, 1][:, None, :], r[:, 0][:, None, :])
+    neg = (r[:, 3][:, None, :] >> k) & 1
+    msg = np.where(neg == 1, -mag, mag) * (k < dc_row[:, None, None])
+    return msg.astype(np.int8).reshape(-1)
 
 
 # ------------------------------------------------------------------ flooding fp32 (strict parity)
@@ -120,7 +134,7 @@ def test_layered_i8_bit_exact_vs_oracle(oracle, key, F, snr, it, mode):
     assert (r.iters == its).all()
     assert (r.ok == D[code.N]).all()
     assert (r.app == app).all(), "APP values differ"
-    assert (r.msgs == rec).all(), "check records (min1, min2, idx, signs) differ"
+    assert (r.msgs == rec).all(), "check-to-variable messages differ"
     assert (r.D == D).all()
 
 

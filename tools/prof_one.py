@@ -11,6 +11,6 @@ geo = {"C1": ("J4_L24_Z96_BlockH.txt", (0, 0, 0), 4.0), "C2": ("J15_L30_Z1280_Bl
 code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", geo[0]), *geo[1])
 y = 1.0 + m.sigma_from_snr(0, geo[2], code.rate) * torch.randn(code.N, F, device="cuda")
 for _ in range(reps):
-    r = code.decode(y, iters, schedule=m.SCHED_LAYERED, out_format=m.OUT_BITPACK, msg_max=31)
+    r = code.decode(y, iters, schedule=m.SCHED_LAYERED, out_format=m.OUT_BITPACK, msg_max=31, beta_num=1, beta_shift=3)
 torch.cuda.synchronize()
 print("ok", float(r.ok.float().mean()))
