@@ -20,6 +20,7 @@
 // min1/min2/first-index on min(|t|, msg_max), m' = m - ((m*beta_num) >> beta_shift), APP =
 // sat127(t + c2v_new)); check-node rule per B/LDPC_Decoder.cu:279-314, schedule ours.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "philox.cuh"
@@ -51,6 +52,11 @@
 #ifndef LDPC_NEG_ALU
 #define LDPC_NEG_ALU 1
 #endif
+//   LDPC_HI_PRELOAD    0  degree buckets above 12 load a row's old messages at the start of the row instead of one
+//                         step ahead: 16-32 fewer live registers in phase 2 (B200, PON: 39.4 -> 41.6 Gbit/s)
+#ifndef LDPC_HI_PRELOAD
+#define LDPC_HI_PRELOAD 0
+#endif
 #ifndef LDPC_LOAD_DEPTH
 #define LDPC_LOAD_DEPTH 8
 #endif
@@ -79,6 +85,8 @@ struct LayeredParams {
     const unsigned char *ch_cw;
     int scale_on;           // beta_num != 0
     unsigned c65;           // 0x65656565: kept in a register so PRMT can take the selector as its immediate
+    unsigned c9b;           // 0x9B009B00 = -0x6500 per lane: VIADDMNMX's addend (as a literal it is re-materialised
+                            // by a move before every use: +2.6 % on B200)
     // kernel-ready layer tables: entry e = {byte offset (c*Z + s)*4 of row 0's bit, wrap threshold (Z - s)*4}
     int2 tab[kMaxBlocks];
     unsigned short off[kMaxLayers];
@@ -190,10 +198,12 @@ template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const LayeredParams &p, int off, int dc_rt,
                                               int Z4, uint4 *msgp, const uint4 *nx, bool ld_next,
                                               unsigned (&mw)[MsgLayout<DCHI>::WORDS], __half2 amaxp, __half2 bmul,
-                                              __half2 nbias)
+                                              __half2 nbias, unsigned c9b)
 {
     constexpr int CH = MsgLayout<DCHI>::CH;
+    constexpr bool PRELOAD = LDPC_HI_PRELOAD || DCHI <= 12;
     const int dc = EXACT ? DC : dc_rt;
+    if (!PRELOAD && !FIRST && EXACT) msg_load<CH>(msgp, mw);
     const __half2 kbias = __float2half2_rn(1407.0f), one = __float2half2_rn(1.0f);
     const __half2 sent = __float2half2_rn(2047.0f);
     unsigned addr[DC];
@@ -240,7 +250,7 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
     }
     // the old messages are dead: start the load of the next step's block, the row finalisation and the whole
     // phase 2 before its first use
-    if (ld_next) msg_load<CH>(nx, mw);
+    if (PRELOAD && ld_next) msg_load<CH>(nx, mw);
     __half2 min1[2], dnew[2], m1p1[2];
     unsigned pm1[2];
 #pragma unroll
@@ -270,7 +280,7 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
                 const __half2 nb = __hfma2(mag, u2h(sg), kbias);
                 const __half2 x = __hadd2(nb, t);
                 // pattern(x) = 0x6400 + (APP_new + 383): subtract 0x6500, clamp to [0, 254]
-                v[h] = __viaddmin_s16x2_relu(h2u(x), 0x9B009B00u, 0x00FE00FEu);
+                v[h] = __viaddmin_s16x2_relu(h2u(x), c9b, 0x00FE00FEu);
                 nbw[h] = h2u(nb);
             }
             sts32(addr[k], prmt(v[0], v[1], 0x6420u));
@@ -301,7 +311,7 @@ __device__ __forceinline__ bool next_block(const uint4 *msgl, const uint4 *nxl, 
 // that its register needs do not leak into the allocation of the hot exact-degree paths.
 template <int DCHI, bool FIRST>
 __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p, int off, int dc, uint4 *msgl,
-                                          __half2 amaxp, __half2 bmul, __half2 nbias)
+                                          __half2 amaxp, __half2 bmul, __half2 nbias, unsigned c9b)
 {
     constexpr int RS = MsgLayout<DCHI>::STRIDE;
     const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
@@ -309,7 +319,7 @@ __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p
         unsigned mw[MsgLayout<DCHI>::WORDS];  // out of line: this path loads its messages itself
         if (!FIRST) msg_load<MsgLayout<DCHI>::CH>(msgl + (size_t)i * RS, mw);
         process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, msgl + (size_t)i * RS, nullptr,
-                                                false, mw, amaxp, bmul, nbias);
+                                                false, mw, amaxp, bmul, nbias, c9b);
     }
 }
 
@@ -317,7 +327,7 @@ __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p
 template <int DCHI, bool FIRST>
 __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams &p, uint4 *msgs, bool last,
                                              unsigned (&mw)[MsgLayout<DCHI>::WORDS], __half2 amaxp, __half2 bmul,
-                                             __half2 nbias)
+                                             __half2 nbias, unsigned c9b)
 {
     constexpr int RS = MsgLayout<DCHI>::STRIDE;
     const int tid = threadIdx.x, T = blockDim.x, Z = p.Z, Z4 = 4 * Z;
@@ -333,7 +343,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         const uint4 *nx;                                                                                      \
         const bool ldn = next_block<DCHI, FIRST>(msgl, nxl, i, T, Z, next_layer_reads, nx);                   \
         process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, msgl + (size_t)i * RS, nx, ldn, \
-                                              mw, amaxp, bmul, nbias);                                        \
+                                              mw, amaxp, bmul, nbias, c9b);                                   \
     }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
@@ -348,8 +358,9 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         } else if (DCHI >= 6 && dc == DCHI - 5) {  // (J20 / J40 / J48_L60_Z160 ran 2x slower through the generic one)
             LDPC_ROWS((DCHI >= 6 ? DCHI - 5 : 1))
         } else {  // degree outside the bucket's exact range: predicated generic path (rare, kept out of line)
-            generic_rows<DCHI, FIRST>(sbase, p, off, dc, msgl, amaxp, bmul, nbias);
-            if (next_layer_reads && tid < Z) msg_load<MsgLayout<DCHI>::CH>(nxl + (size_t)tid * RS, mw);
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, msgl, amaxp, bmul, nbias, c9b);
+            if ((LDPC_HI_PRELOAD || DCHI <= 12) && next_layer_reads && tid < Z)
+                msg_load<MsgLayout<DCHI>::CH>(nxl + (size_t)tid * RS, mw);
         }
 #undef LDPC_ROWS
         __syncthreads();
@@ -439,9 +450,17 @@ template <int DCMAX>
 struct ThreadCap {
     static constexpr int value = DCMAX <= 12 ? 640 : (DCMAX <= 24 ? 512 : 384);
 };
+// __launch_bounds__ of the kernel = its register cap (640 -> 96, 512 -> 128, 384 -> 168 registers).  Buckets 16 and
+// 20 take 96 registers although their arrays want more: the shipped codes there have small Z (J4_L24_Z96: 96
+// threads per CTA), where two more resident CTAs per SM beat the ~0.3 KB of spills (B200: 45.6 -> 47.5 Gbit/s);
+// bucket 24 (PON, Z = 256, two CTAs per SM by shared memory either way) keeps 128 (39.4 vs 38.0 at 96).
+template <int DCMAX>
+struct RegCapThreads {
+    static constexpr int value = (DCMAX > 12 && DCMAX <= 20) ? 640 : ThreadCap<DCMAX>::value;
+};
 
 template <int DCMAX>
-__global__ void __launch_bounds__(ThreadCap<DCMAX>::value, 1)
+__global__ void __launch_bounds__(RegCapThreads<DCMAX>::value, 1)
 ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -456,6 +475,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     uint4 *rec = p.rec + (size_t)blockIdx.x * p.M * MsgLayout<DCMAX>::STRIDE;
     const __half2 amaxp = __float2half2_rn(p.msg_max);  // magnitude clip of min1 / min2
+    const unsigned c9b = p.c9b;
     const __half2 bmul = __float2half2_rn(p.beta_mul);
     const __half2 nbias = __float2half2_rn(-p.beta_bias);
 
@@ -618,9 +638,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         while (it < p.iters) {
             it++;
             if (it == 1)
-                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias);
+                sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias, c9b);
             else
-                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias);
+                sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias, c9b);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 // The pass stops after the first layer that leaves every running frame with a failed check (the
                 // usual case until the last iterations: one layer of J is read instead of all) — the outcome
@@ -711,6 +731,8 @@ static int plan_i8(const ldpc_code *c, int F, I8Plan *pl)
         default: return LDPC_ERR_UNSUPPORTED;
     }
     // threads: the Z rows of a layer spread over whole warps, at most ThreadCap<DCHI> threads
+    if (const char *e = getenv("LDPC_B200_THREADS"))  // tuning knob (tools/ab): CTA width cap
+        if (atoi(e) >= 32 && atoi(e) < cap) cap = atoi(e);
     const int rows_per_thread = (c->Z + cap - 1) / cap;
     const int threads = (c->Z + rows_per_thread - 1) / rows_per_thread;
     pl->threads = (threads + 31) & ~31;
@@ -782,6 +804,7 @@ int launch_layered_i8(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st,
     p.ch_cw = a.ch_cw;
     p.scale_on = a.beta_num != 0;
     p.c65 = 0x65656565u;
+    p.c9b = 0x9B009B00u;
     p.lt = c->lt;
     for (int r = 0; r < c->J; r++) {
         p.off[r] = c->lt.off[r];
