@@ -10,8 +10,11 @@ min-sum with int8 state, 10 iterations fixed, no early exit.  One step = one pas
 shard of the frame range (weak scaling, no data-path collective); the time is the max over ranks.
 
 Printed JSON line: value (device-resident I/O), e2e (same call with HOST buffers, H2D/D2H inside the
-timed region), roofline (SURVEY §8d byte model over the kernel's CUDA-event time), cpu_baseline
-(the C oracle on the host cores, bounded sample), clocks, gpu_launches.
+timed region, results compared byte for byte with the device-resident ones: e2e.parity_ok), sustained
+(>= 3 s back to back), roofline (SURVEY §8d byte model over the kernel's CUDA-event time; traffic from the
+tracked ncu summary), clocks, gpu_launches, and at N = 1 also configs (C1 / C3 / flooding fp32),
+reference_gpu (the reference's own GPU decoder on this box) and cpu_baseline (the C oracle on the host
+cores, bounded sample).
 --impl reference times the reference's own decoder sources compiled for the CPU (oracle/_ref).
 """
 import argparse
@@ -33,9 +36,6 @@ ITERS = 10
 EBN0_DB = 2.0
 # B_cw(it) = it*(2*E*w + 2*M*rec) + N*4 + N/8, int8: w = 1, rec = 4  -> 4 638 400 B at 10 it
 B_CW = ITERS * (2 * E * 1 + 2 * M * 4) + N * 4 + N // 8
-# dram__bytes_read.sum + dram__bytes_write.sum of one ldpc_layered_i8_kernel launch over 2368 frames, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_layered_i8_summary.txt (1.49 GB + 3.29 GB): per frame
-NCU_DRAM_BYTES_PER_FRAME = (1.486490e9 + 3.289583e9) / 2368
 METRIC = "decoded info Gbit/s at fixed iters"
 WORKLOAD = ("binary QC-LDPC J15_L30_Z1280 (N=38400, K=19200), BPSK-AWGN Eb/N0 2.0 dB, layered normalised "
             "min-sum (x0.875), int8 state, 10 iterations fixed, no early exit")
@@ -175,10 +175,134 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ our arm
 
+# The three binary configs of BASELINE.json: geometry, edges, largest check degree, frames per launch,
+# operating point (snrtype, dB).  B_cw(it) = it*(2*E*w + 2*M*rec) + N*4 + N/8 with w = 1, rec = 2*w + 1 + ceil(dc_max/8).
+CONFIGS = {
+    "C1": dict(file="J4_L24_Z96_BlockH.txt", geo=(4, 24, 96), E=7680, dc_max=20, F=65536, snr=(1, 3.0)),
+    "C2": dict(file=CODE_FILE, geo=(J, L, Z), E=E, dc_max=8, F=148 * 4 * 16, snr=(0, EBN0_DB)),
+    "C3": dict(file="PON_LDPC.txt", geo=(12, 69, 256), E=70400, dc_max=23, F=16384, snr=(1, 4.5)),
+}
+
+
+def b_cw_int8(cfg, iters):
+    j, l, z = cfg["geo"]
+    n, m_ = l * z, j * z
+    rec = 2 + 1 + (cfg["dc_max"] + 7) // 8
+    return iters * (2 * cfg["E"] + 2 * m_ * rec) + n * 4 + n // 8
+
+
+def b_cw_flooding_fp32(cfg, iters):
+    """the reference's own layout: (4E + 2N) * 4 bytes per codeword-iteration"""
+    j, l, z = cfg["geo"]
+    return iters * (4 * cfg["E"] + 2 * l * z) * 4
+
+
+def ncu_traffic_per_frame():
+    """dram bytes per frame of the dominant kernel, from the tracked ncu summary written by tools/ncu_summary.py --json"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_layered_i8.json")) as f:
+            d = json.load(f)["C2"]
+        return (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / d["frames"], "profiles/r02_ncu_layered_i8.json"
+    except Exception:
+        return None, None
+
+
+def timed_launches(fn, steps, torch):
+    """CUDA events on the launching stream around every step; returns (total ms, mean ms per step)"""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    n = 0
+    for i in range(steps):
+        n += fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[-1]), sum(ev[i].elapsed_time(ev[i + 1]) for i in range(steps)) / steps, n
+
+
+def other_configs(m, torch, dev, peak, kw):
+    """C1 / C3 layered int8 at 10 fixed iterations, C3 throughput mode, and the same-arithmetic figure (flooding fp32,
+    the reference's schedule, layout and update rule) — N = 1 only, informational beside the headline."""
+    res = []
+    for name in ("C1", "C3"):
+        cfg = CONFIGS[name]
+        code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])
+        F = cfg["F"]
+        sigma = m.sigma_from_snr(cfg["snr"][0], cfg["snr"][1], code.rate)
+        y = (1.0 + sigma * torch.randn(code.N, F, device=dev)).contiguous()
+        out = torch.empty(code.out_bytes(F, m.OUT_BITPACK), dtype=torch.uint8, device=dev)
+        it_d = torch.empty(F, dtype=torch.int32, device=dev)
+        ok_d = torch.empty(F, dtype=torch.int32, device=dev)
+        step = lambda **x: code.decode(y, x.pop("iters", ITERS), out=out, iters_out=it_d, ok_out=ok_d, **dict(kw, **x)).launches
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        _, ms, _ = timed_launches(step, 10, torch)
+        ach = F * b_cw_int8(cfg, ITERS) / (ms * 1e-3) / 1e9
+        res.append({"config": name, "mode": "layered int8, 10 iterations fixed", "frames_per_launch": F,
+                    "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms,
+                    "roofline_frac": ach / peak, "b_cw_bytes": b_cw_int8(cfg, ITERS)})
+        if name == "C3":  # BASELINE.json configs[2]: throughput mode = syndrome early termination, max 50 iterations
+            step2 = lambda: step(iters=50, early_exit=m.EXIT_SYNDROME)
+            for _ in range(3):
+                step2()
+            torch.cuda.synchronize()
+            _, ms2, _ = timed_launches(step2, 10, torch)
+            res.append({"config": "C3", "mode": "layered int8, syndrome early termination, max 50 iterations, Es/N0 4.5 dB",
+                        "frames_per_launch": F, "value": F * code.K / (ms2 * 1e-3) / 1e9, "unit": "Gbit/s",
+                        "kernel_ms": ms2, "avg_iterations": float(it_d.float().mean().item()),
+                        "converged_fraction": float(ok_d.float().mean().item())})
+        del y, out
+    for name, F in (("C1", 4096), ("C2", 1024)):  # flooding fp32: the reference's arithmetic, F = 4096 is its batch
+        cfg = CONFIGS[name]
+        code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])
+        sigma = m.sigma_from_snr(cfg["snr"][0], cfg["snr"][1], code.rate)
+        y = (1.0 + sigma * torch.randn(code.N, F, device=dev)).contiguous()
+        out = torch.empty(code.out_bytes(F, m.OUT_INT32_REF), dtype=torch.uint8, device=dev)
+        it_d = torch.empty(F, dtype=torch.int32, device=dev)
+        ok_d = torch.empty(F, dtype=torch.int32, device=dev)
+        step = lambda: code.decode(y, ITERS, out=out, iters_out=it_d, ok_out=ok_d).launches
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        _, ms, nl = timed_launches(step, 5, torch)
+        ach = F * b_cw_flooding_fp32(cfg, ITERS) / (ms * 1e-3) / 1e9
+        res.append({"config": name, "mode": "flooding fp32 un-normalised min-sum, 10 iterations (the reference's rules and "
+                    "Memory_RQ layout: same arithmetic as the reference arm)", "frames_per_launch": F,
+                    "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "ms_per_step": ms, "launches_per_step": nl // 5,
+                    "roofline_frac": ach / peak, "bytes_model": "(4E + 2N) * 4 B per codeword-iteration"})
+        del y, out
+    return res
+
+
+def reference_gpu():
+    """The reference's own GPU decoder on this box (baseline/_ref/bldpc_gpu_C2_time, built from /root/reference by
+    baseline/build_all.sh): live if the binary travelled here, else the tracked measurement of the same command."""
+    exe = os.path.join(ROOT, "baseline", "_ref", "bldpc_gpu_C2_time")
+    try:
+        if os.path.exists(exe):
+            p = subprocess.run([exe, "time", str(EBN0_DB), "2"], capture_output=True, text=True, timeout=240)
+            for ln in p.stdout.splitlines():
+                if ln.startswith("{"):
+                    d = json.loads(ln)
+                    d["source"] = "live: baseline/_ref/bldpc_gpu_C2_time"
+                    return d
+        with open(os.path.join(ROOT, "profiles", "r02_reference_gpu.jsonl")) as f:
+            for ln in f:
+                d = json.loads(ln)
+                if d.get("binary") == "C2_time":
+                    d["source"] = "profiles/r02_reference_gpu.jsonl (recorded on a B200 of this pool)"
+                    return d
+    except Exception as e:
+        return {"error": repr(e)}
+    return None
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import cuda_ldpc_b200 as m
+    from cuda_ldpc_b200 import sim as simlib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,92 +338,114 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # clocks / throttle reasons are sampled from the warm-up to the end of the e2e region (nvidia-smi answers in
-    # ~50 ms, the device-timed region alone lasts ~0.2 s), all of it under decode load
+    # ~50 ms, the K-step device-timed region alone lasts ~0.15 s), all of it under decode load
     clk = ClockSampler(local)
     clk.__enter__()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    launches = 0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    total_ms, kern_ms, launches = timed_launches(step, args.steps, torch)
     barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        launches += step()
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)) / args.steps  # one launch per step
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = allmax(total_ms)
     value = world * F * args.steps * K / (total_ms * 1e-3) / 1e9
     ok_frac = float(ok_d.float().mean().item())
 
+    # ---- sustained: the same step back to back for >= 3 s (does the kernel hold its clock?)
+    sus_clk = ClockSampler(local)
+    sus_clk.__enter__()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_sus = max(int(args.sustain_s * 1e3 / kern_ms), 1)
+    e0.record()
+    for _ in range(n_sus):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    sus_ms = allmax(e0.elapsed_time(e1))
+    sus_clk.__exit__()
+    sustained = {"value": world * F * n_sus * K / (sus_ms * 1e-3) / 1e9, "unit": "Gbit/s", "seconds": sus_ms * 1e-3,
+                 "steps": n_sus, "clocks": sus_clk.summary()}
+    dev_res = (out.clone(), it_d.clone(), ok_d.clone())  # device-resident result of this input: the e2e parity reference
+
     # ---- e2e: the same C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
-    Fe = args.e2e_frames
-    yh = y[:, :Fe].contiguous().cpu().pin_memory().numpy()
+    Fe = F
+    yh = y.cpu().pin_memory().numpy()
     e2e_steps = max(2, min(args.steps, 4))
-    # pinned result buffers (hard bits, iterations, flags): the step's result is read back into them
     ho = torch.empty(code.out_bytes(Fe, m.OUT_BITPACK), dtype=torch.uint8).pin_memory().numpy()
     hi = torch.empty(Fe, dtype=torch.int32).pin_memory().numpy()
     hk = torch.empty(Fe, dtype=torch.int32).pin_memory().numpy()
     hkw = dict(kw, out=ho, iters_out=hi, ok_out=hk)
-    code.decode(yh, ITERS, **hkw)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = code.decode(yh, ITERS, **hkw)
-        launches_e2e = r.launches
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * Fe * e2e_steps * K / float(te.item()) / 1e9
-    h2d = Fe * code.N * 4
-    d2h = code.out_bytes(Fe, m.OUT_BITPACK) + 8 * Fe
-    # same call with the host buffer in the [F][N] layout: frame chunks are contiguous, so the library
-    # overlaps the H2D copy of chunk k+1 with the decode of chunk k (informational, not the headline)
-    yh_fn = y[:, :Fe].t().contiguous().cpu().pin_memory().numpy()
-    code.decode(yh_fn, ITERS, layout=m.LAYOUT_FN, **hkw)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        code.decode(yh_fn, ITERS, layout=m.LAYOUT_FN, **hkw)
-    torch.cuda.synchronize()
-    e2e_fn_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
-    del yh_fn
-    # context for "PCIe-bound": the same call fed fp16 channel values (half the bytes; NOT the reference's input type)
-    yh16 = torch.from_numpy(yh).to(torch.float16).pin_memory().numpy()
-    code.decode(yh16, ITERS, **hkw)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        code.decode(yh16, ITERS, **hkw)
-    torch.cuda.synchronize()
-    e2e_fp16_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
-    del yh16
-    # and with host-side int8 packing of the chunks (ldpc_decode_opts_t::host_pack_threads): a quarter of the PCIe
-    # bytes, same bits, but it occupies the host cores — informational; only tried when this rank has >= 12 of them
-    pack_threads = (os.cpu_count() or 1) // world
-    e2e_pack_val = None
-    if pack_threads >= 12:
-        code.decode(yh, ITERS, host_pack_threads=pack_threads, **hkw)
+    cpus = len(os.sched_getaffinity(0))
+    # host quantiser threads: the library's automatic choice when this process has the host to itself; an explicit
+    # share of the cores when several ranks run on one box (< 8 per rank: plain fp32 copy)
+    pack = 0 if world == 1 else ((os.cpu_count() or 1) // world if (os.cpu_count() or 1) // world >= 8 else -1)
+
+    def host_parity():
+        return bool((torch.from_numpy(ho).to(dev) == dev_res[0]).all().item() and
+                    (torch.from_numpy(hi).to(dev) == dev_res[1]).all().item() and
+                    (torch.from_numpy(hk).to(dev) == dev_res[2]).all().item())
+
+    def time_host(n, **extra):
+        code.decode(yh, ITERS, **dict(hkw, **extra))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            code.decode(yh, ITERS, host_pack_threads=pack_threads, **hkw)
+        for _ in range(n):
+            r = code.decode(yh, ITERS, **dict(hkw, **extra))
         torch.cuda.synchronize()
-        e2e_pack_val = Fe * e2e_steps * K / (time.perf_counter() - t0) / 1e9
+        return time.perf_counter() - t0, r.launches
+
+    packed = pack > 0 or (pack == 0 and cpus >= 12)  # the library's own rule (csrc/bldpc_api.cu pack_threads_of)
+    e2e_s, launches_e2e = time_host(e2e_steps, host_pack_threads=pack)
+    parity_ok = host_parity()
+    e2e_val = world * Fe * e2e_steps * K / allmax(e2e_s) / 1e9
+    h2d = Fe * code.N * 4
+    d2h = code.out_bytes(Fe, m.OUT_BITPACK) + 8 * Fe
+    ho[:] = 0
+    copy_s, _ = time_host(e2e_steps, host_pack_threads=-1)  # the same call with the quantiser off: fp32 over PCIe
+    parity_ok = parity_ok and host_parity()
+    e2e_copy_val = world * Fe * e2e_steps * K / allmax(copy_s) / 1e9
+
+    # ---- the other two end-to-end shapes of the reference's loop
+    # (b) the reference's actual interface (B/LDPC_Decoder.cuh:5): Channel_Out is a DEVICE pointer, D comes back to the host
+    def step_dev_in_host_out():
+        n = code.decode(y, ITERS, out=out, iters_out=it_d, ok_out=ok_d, **kw).launches
+        torch.from_numpy(ho).copy_(out, non_blocking=True)
+        torch.from_numpy(hi).copy_(it_d, non_blocking=True)
+        torch.from_numpy(hk).copy_(ok_d, non_blocking=True)
+        return n
+    step_dev_in_host_out()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_dev_in_host_out()
+    torch.cuda.synchronize()
+    e2e_b = world * Fe * e2e_steps * K / allmax(time.perf_counter() - t0) / 1e9
+    parity_ok = parity_ok and host_parity()
+    # (c) the simulation-loop shape (B/Simulation.cu:111-156): no input at all — the channel is generated inside the
+    # kernel (LDPC_DTYPE_CHANNEL), Statistic runs on the device, 48 bytes of counters come back per batch
+    runner = simlib.CudaBatchRunner(code, F, maxit=ITERS, early_exit=m.EXIT_NONE, msg_max=args.msg_max,
+                                    llr_scale=args.llr_scale, beta_num=args.beta_num, beta_shift=args.beta_shift)
+    runner.run(sigma, rank * F)
+    runner.counters()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        runner.run(sigma, (i * world + rank) * F)
+        cnt = runner.counters()  # D2H of the six int64 counters + sync
+    e2e_c = world * Fe * e2e_steps * K / allmax(time.perf_counter() - t0) / 1e9
     clk.__exit__()
 
     if rank == 0:
         peak, which = measured_peaks()
         achieved = F * B_CW / (kern_ms * 1e-3) / 1e9
+        tpf, tsrc = ncu_traffic_per_frame()
         line = {
             "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -309,42 +455,66 @@ def run_ours(args):
                        "input": "fp32 [N][F] channel values resident in HBM (1.45 GB per step at F=9472, larger than L2)",
                        "output": "bit-packed hard decisions + per-frame syndrome flag",
                        "converged_fraction": ok_frac},
-            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_step": Fe, "steps": e2e_steps, "launches_per_step": launches_e2e,
-                    "cpu_affinity": numa,
-                    "layout": "[N][F] fp32 pinned host buffer (the reference's Channel_Out layout); the library cuts "
-                              "the batch into chunks of 2 groups per SM on two streams (H2D / decode / D2H overlap)",
-                    "rank0_value_with_FN_layout_chunked_overlap": e2e_fn_val,
-                    "rank0_value_with_host_int8_packing": e2e_pack_val, "host_pack_threads": pack_threads,
-                    "rank0_value_with_fp16_host_input": e2e_fp16_val},
+            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * code.N if packed else h2d,
+                    "d2h_bytes_per_step": d2h, "frames_per_step": Fe, "steps": e2e_steps,
+                    "launches_per_step": launches_e2e, "cpu_affinity": numa, "parity_ok": parity_ok,
+                    "parity_check": "hard bits, iteration counts and flags of every host-buffer shape below == the "
+                                    "device-resident result of the same frames, byte for byte",
+                    "layout": "[N][F] fp32 pinned host buffer (the reference's Channel_Out layout) through "
+                              "ldpc_decode_batch(mem_space = HOST): chunks of 2 groups per SM on two streams; each chunk is "
+                              "quantised to int8 by the library's host threads (the kernel's own rule, bit-identical) while "
+                              "the previous chunk is copied and decoded" if packed else
+                              "[N][F] fp32 pinned host buffer copied as fp32 (too few host cores per rank for the quantiser)",
+                    "host_pack_threads": "auto" if pack == 0 else pack, "host_cpus": cpus,
+                    "host_bytes_read_per_step": Fe * code.N * 4,
+                    "value_with_fp32_copy_over_pcie": e2e_copy_val,
+                    "shape_device_in_host_out": {"value": e2e_b, "unit": "Gbit/s", "what": "Channel_Out on the device (the "
+                                                 "reference's own interface, B/LDPC_Decoder.cuh:5), hard decisions + "
+                                                 "iterations + flags read back to pinned host memory every step",
+                                                 "d2h_bytes_per_step": d2h},
+                    "shape_sim_loop": {"value": e2e_c, "unit": "Gbit/s", "what": "fused device channel (LDPC_DTYPE_CHANNEL) -> "
+                                       "decode -> ldpc_statistic -> 48 bytes of counters to the host per batch "
+                                       "(B/Simulation.cu:111-156 without its F*N buffers)", "d2h_bytes_per_step": 48,
+                                       "counters_last_batch": [int(v) for v in cnt]}},
             "gpu_launches": launches,
             "clocks": clk.summary(),
+            "sustained": sustained,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic if args.traffic is not None else NCU_DRAM_BYTES_PER_FRAME * F,
-                         "traffic_source": "ncu --set full at F=2368 (profiles/r01_ncu_layered_i8_summary.txt), scaled "
-                                           "to this launch's frame count; mostly check records spilling from L2",
+                         "traffic": args.traffic if args.traffic is not None else (tpf * F if tpf else None),
+                         "traffic_source": tsrc and f"{tsrc}: ncu --set full of this kernel, dram bytes per frame x {F} frames "
+                                                    "(mostly c2v message blocks spilling from L2)",
                          "peak_source": f"{which} (MEASURED_PEAKS.json, burst copy)",
-                         "kernel": "ldpc_layered_i8_kernel", "kernel_ms": kern_ms,
+                         "kernel": "ldpc_layered_i8_kernel<8>", "kernel_ms": kern_ms,
                          "bytes_model": f"SURVEY 8(d): B_cw(10)={B_CW} B x {F} frames per launch (algorithmic bytes of a "
                                         "streaming layered decoder).  This design keeps the APP state in shared "
-                                        "memory, so its real DRAM traffic is lower (traffic) and the pipe that binds is "
-                                        "the SM issue rate, not HBM: see issue_bound",
-                         "issue_bound": {"inst_per_edge_4frames": 57.5, "ipc_per_smsp": 0.71,
-                                         "practical_ipc_peak_per_smsp": 0.80,
-                                         "source": "profiles/r01_ncu_layered_i8_summary.txt, profiles/r01_pipe_ubench.txt"}},
+                                        "memory, so its real DRAM traffic is lower (traffic) and the pipes that bind are "
+                                        "the SM's ALU / FMA issue pipes: profiles/r02_ncu_layered_i8_summary.txt"},
         }
-        try:
-            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline uses every host core again
-        except Exception:
-            pass
-        try:
-            line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_port()
-        except Exception as e:  # the bench value never depends on the oracle
-            line["cpu_baseline"] = {"error": repr(e)}
+        if world == 1:
+            try:
+                line["configs"] = [{"config": "C2", "mode": "layered int8, 10 iterations fixed (the headline)",
+                                    "frames_per_launch": F, "value": value, "unit": "Gbit/s", "kernel_ms": kern_ms,
+                                    "roofline_frac": achieved / peak, "b_cw_bytes": B_CW}] + other_configs(m, torch, dev, peak, kw)
+            except Exception as e:
+                line["configs"] = {"error": repr(e)}
+            line["reference_gpu"] = reference_gpu()
+            try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline uses every host core again
+            except Exception:
+                pass
+            try:
+                line["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_port()
+            except Exception as e:  # the bench value never depends on the oracle
+                line["cpu_baseline"] = {"error": repr(e)}
+        else:
+            # rank 0's OpenMP team would fight the other ranks' spin-waits (round 1: 30x too slow): N = 1 only
+            line["cpu_baseline"] = None
         print(json.dumps(line))
+        if not parity_ok:
+            print("e2e parity check FAILED: host-buffer results differ from the device-resident results", file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 0 if parity_ok else 3
 
 
 def main():
@@ -354,7 +524,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=148 * 4 * 16)
-    ap.add_argument("--e2e-frames", type=int, default=148 * 4 * 16)
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the back-to-back sustained region")
     ap.add_argument("--msg-max", type=int, default=31)
     ap.add_argument("--llr-scale", type=float, default=8.0)
     ap.add_argument("--beta-num", type=int, default=1)

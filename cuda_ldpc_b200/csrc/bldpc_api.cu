@@ -96,6 +96,19 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // buffers) is needed for real overlap; pageable memory still works (the copies then serialise).
 extern "C" void ldpcb_host_pack_nf(const float *y, size_t ldF, int N, int f0, int fc, float scale, signed char *out,
                                    int threads);  // host_pack.cc
+extern "C" int ldpcb_host_cpus(void);
+
+// ldpc_decode_opts_t::host_pack_threads -> threads of the host quantiser (0 = copy the fp32 values)
+static int pack_threads_of(const ldpc_decode_opts_t *o)
+{
+    if (o->llr_dtype != LDPC_DTYPE_FP32 || o->layout != LDPC_LAYOUT_NF) return 0;
+    if (o->host_pack_threads > 0) return o->host_pack_threads;
+    if (o->host_pack_threads < 0) return 0;
+    // auto: the quantiser beats the fp32 copy once it reads host DRAM faster than PCIe moves it (~55 GB/s), which
+    // takes about a dozen cores (profiles/r02_e2e.txt); fewer CPUs in this process' affinity mask -> plain copy
+    const int cpus = ldpcb_host_cpus();
+    return cpus >= 12 ? (cpus > 32 ? 32 : cpus) : 0;
+}
 
 // pinned staging slots of the host-pack path, grown on demand
 static int ensure_pack_slots(const ldpc_code *cc, size_t bytes)
@@ -118,50 +131,74 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
                                  const ldpc_decode_opts_t *o, int Fc)
 {
     const int F = o->batch, N = c->N;
-    // host pack: fp32 [N][F] -> int8 chunk on host threads, a quarter of the PCIe bytes, same decode bit for bit
-    const bool pack = o->host_pack_threads >= 1 && o->llr_dtype == LDPC_DTYPE_FP32 && o->layout == LDPC_LAYOUT_NF;
+    // Hybrid feed (fp32 [N][F] input with host threads available): chunks alternate between two ways into the GPU
+    // that run CONCURRENTLY — "pack" chunks are quantised to int8 by host threads (the kernel's own rule, a quarter
+    // of the PCIe bytes, same decode bit for bit) while the DMA engine copies the previous "copy" chunk as fp32.
+    // Host cores reading DRAM and PCIe each sustain 50-60 GB/s on the B200 box; neither alone beats the other
+    // (profiles/r02_e2e.txt), together they add up to 70-80 GB/s.  copy chunk = 1/2 of a pack chunk by default (swept 0-150 %): the
+    // DMA engine also moves the pack chunks' int8 bytes (tuning: LDPC_B200_HYBRID_COPY_PCT, 0 = pack every chunk).
+    const int pack_threads = pack_threads_of(o);
+    const bool pack = pack_threads >= 1;
+    int copy_pct = 50;
+    if (const char *e = getenv("LDPC_B200_HYBRID_COPY_PCT")) copy_pct = atoi(e) < 0 ? 0 : (atoi(e) > 400 ? 400 : atoi(e));
+    int Fcopy = pack ? ((int)((long long)Fc * copy_pct / 100) & ~3) : Fc;  // frames of a copy chunk (whole groups)
     if (pack) {
         int rcp = ensure_pack_slots(c, (size_t)N * Fc);
         if (rcp != LDPC_OK) return rcp;
     }
-    const size_t esz = pack ? 1 : dtype_bytes(o->llr_dtype);
+    const size_t esz = dtype_bytes(o->llr_dtype);
     const int W = (N + 31) / 32;
+    const int Fmax = Fc > Fcopy ? Fc : Fcopy;
     size_t rec_bytes = 0;
-    int rc = layered_i8_scratch_bytes(c, Fc, o->beta_num, &rec_bytes);
+    int rc = layered_i8_scratch_bytes(c, Fmax, o->beta_num, &rec_bytes);
     if (rc != LDPC_OK) return rc;
-    const size_t in_b = align_up((size_t)N * Fc * esz), out_b = align_up(ldpc_out_bytes(c, Fc, o->out_format));
-    const size_t fl_b = align_up((size_t)Fc * 4), slot = in_b + out_b + 2 * fl_b + align_up(rec_bytes);
+    const size_t in_b = align_up((size_t)N * Fmax * esz), out_b = align_up(ldpc_out_bytes(c, Fmax, o->out_format));
+    const size_t fl_b = align_up((size_t)Fmax * 4), slot = in_b + out_b + 2 * fl_b + align_up(rec_bytes);
     unsigned char *base = nullptr;
     rc = ensure_scratch(c, 2 * slot, reinterpret_cast<void **>(&base));
     if (rc != LDPC_OK) return rc;
     cudaStream_t user = reinterpret_cast<cudaStream_t>(o->stream);
     LDPC_CUDA_TRY(cudaStreamSynchronize(user));  // work queued before this call is complete
-    int launches = 0;
-    for (int f0 = 0, k = 0; f0 < F; f0 += Fc, k++) {
-        const int fc = (F - f0 < Fc) ? F - f0 : Fc;
+    int launches = 0, npack = 0;
+    rc = LDPC_OK;
+    for (int f0 = 0, k = 0; f0 < F && rc == LDPC_OK; k++) {
+        // even k: pack chunk (stream 0, slot 0), odd k: copy chunk (stream 1, slot 1); without host threads every chunk
+        // is a copy chunk and the two streams / slots simply alternate
+        const bool packed = pack && ((k & 1) == 0 || Fcopy == 0);
+        const int want = packed ? Fc : (pack ? Fcopy : Fc);
+        const int fc = (F - f0 < want) ? F - f0 : want;
         cudaStream_t st = c->pipe_stream[k & 1];
         unsigned char *sl = base + (size_t)(k & 1) * slot;
         unsigned char *d_in = sl, *d_out = sl + in_b;
         int *d_it = reinterpret_cast<int *>(sl + in_b + out_b), *d_ok = reinterpret_cast<int *>(sl + in_b + out_b + fl_b);
         const unsigned char *h_in = reinterpret_cast<const unsigned char *>(llr);
-        if (pack) {
-            // the slot was last read by the copy of chunk k-2: wait for it, quantise chunk k into it (the GPU is
-            // busy with chunk k-1 meanwhile), copy the contiguous [N][fc] block
-            if (k >= 2) LDPC_CUDA_TRY(cudaEventSynchronize(c->pack_ev[k & 1]));
-            signed char *stage = reinterpret_cast<signed char *>(c->pack_host[k & 1]);
-            ldpcb_host_pack_nf(reinterpret_cast<const float *>(llr), (size_t)F, N, f0, fc, o->llr_scale, stage,
-                               o->host_pack_threads);
-            LDPC_CUDA_TRY(cudaMemcpyAsync(d_in, stage, (size_t)N * fc, cudaMemcpyHostToDevice, st));
-            LDPC_CUDA_TRY(cudaEventRecord(c->pack_ev[k & 1], st));
+        cudaError_t ce = cudaSuccess;
+        if (packed) {
+            // the staging buffer was last read by the copy of the pack chunk before last: wait for it, quantise this
+            // chunk into it (the GPU and the DMA engine are busy with the previous chunks meanwhile)
+            const int sb = npack & 1;
+            if (npack >= 2) ce = cudaEventSynchronize(c->pack_ev[sb]);
+            signed char *stage = reinterpret_cast<signed char *>(c->pack_host[sb]);
+            if (ce == cudaSuccess) {
+                ldpcb_host_pack_nf(reinterpret_cast<const float *>(llr), (size_t)F, N, f0, fc, o->llr_scale, stage,
+                                   pack_threads);
+                ce = cudaMemcpyAsync(d_in, stage, (size_t)N * fc, cudaMemcpyHostToDevice, st);
+            }
+            if (ce == cudaSuccess) ce = cudaEventRecord(c->pack_ev[sb], st);
+            npack++;
         } else if (o->layout == LDPC_LAYOUT_NF)
-            LDPC_CUDA_TRY(cudaMemcpy2DAsync(d_in, (size_t)fc * esz, h_in + (size_t)f0 * esz, (size_t)F * esz,
-                                            (size_t)fc * esz, N, cudaMemcpyHostToDevice, st));
+            ce = cudaMemcpy2DAsync(d_in, (size_t)fc * esz, h_in + (size_t)f0 * esz, (size_t)F * esz, (size_t)fc * esz, N,
+                                   cudaMemcpyHostToDevice, st);
         else
-            LDPC_CUDA_TRY(cudaMemcpyAsync(d_in, h_in + (size_t)f0 * N * esz, (size_t)fc * N * esz,
-                                          cudaMemcpyHostToDevice, st));
+            ce = cudaMemcpyAsync(d_in, h_in + (size_t)f0 * N * esz, (size_t)fc * N * esz, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) {
+            set_cuda_error(ce, "host chunk upload");
+            rc = LDPC_ERR_CUDA;
+            break;
+        }
         LayeredArgs a;
         a.llr = d_in;
-        a.llr_dtype = pack ? LDPC_DTYPE_INT8 : o->llr_dtype;
+        a.llr_dtype = packed ? LDPC_DTYPE_INT8 : o->llr_dtype;
         a.layout = o->layout;
         a.F = fc;
         a.iters = iters;
@@ -183,24 +220,37 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
         a.ch_seed = a.ch_first = 0;
         a.ch_cw = nullptr;
         rc = launch_layered_i8(c, a, st, &launches);
-        if (rc != LDPC_OK) return rc;
+        if (rc != LDPC_OK) break;
         unsigned char *h_out = reinterpret_cast<unsigned char *>(hard_bits);
         if (o->out_format == LDPC_OUT_BITPACK) {
-            LDPC_CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)f0 * W * 4, d_out, (size_t)fc * W * 4, cudaMemcpyDeviceToHost, st));
+            ce = cudaMemcpyAsync(h_out + (size_t)f0 * W * 4, d_out, (size_t)fc * W * 4, cudaMemcpyDeviceToHost, st);
         } else if (o->out_format == LDPC_OUT_U8 && o->layout == LDPC_LAYOUT_FN) {
-            LDPC_CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)f0 * N, d_out, (size_t)fc * N, cudaMemcpyDeviceToHost, st));
+            ce = cudaMemcpyAsync(h_out + (size_t)f0 * N, d_out, (size_t)fc * N, cudaMemcpyDeviceToHost, st);
         } else {
             const size_t es = (o->out_format == LDPC_OUT_INT32_REF) ? 4 : 1;
             const int rows = (o->out_format == LDPC_OUT_INT32_REF) ? N + 1 : N;
-            LDPC_CUDA_TRY(cudaMemcpy2DAsync(h_out + (size_t)f0 * es, (size_t)F * es, d_out, (size_t)fc * es,
-                                            (size_t)fc * es, rows, cudaMemcpyDeviceToHost, st));
+            ce = cudaMemcpy2DAsync(h_out + (size_t)f0 * es, (size_t)F * es, d_out, (size_t)fc * es, (size_t)fc * es, rows,
+                                   cudaMemcpyDeviceToHost, st);
         }
-        if (o->iters_out)
-            LDPC_CUDA_TRY(cudaMemcpyAsync(o->iters_out + f0, d_it, (size_t)fc * 4, cudaMemcpyDeviceToHost, st));
-        if (o->ok_out) LDPC_CUDA_TRY(cudaMemcpyAsync(o->ok_out + f0, d_ok, (size_t)fc * 4, cudaMemcpyDeviceToHost, st));
+        if (ce == cudaSuccess && o->iters_out)
+            ce = cudaMemcpyAsync(o->iters_out + f0, d_it, (size_t)fc * 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess && o->ok_out)
+            ce = cudaMemcpyAsync(o->ok_out + f0, d_ok, (size_t)fc * 4, cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) {
+            set_cuda_error(ce, "host chunk download");
+            rc = LDPC_ERR_CUDA;
+            break;
+        }
+        f0 += fc;
     }
-    LDPC_CUDA_TRY(cudaStreamSynchronize(c->pipe_stream[0]));
-    LDPC_CUDA_TRY(cudaStreamSynchronize(c->pipe_stream[1]));
+    // every exit path waits for both internal streams: async copies still target the caller's buffers and the
+    // pinned staging slots
+    const cudaError_t s0 = cudaStreamSynchronize(c->pipe_stream[0]), s1 = cudaStreamSynchronize(c->pipe_stream[1]);
+    if (rc != LDPC_OK) return rc;
+    if (s0 != cudaSuccess || s1 != cudaSuccess) {
+        set_cuda_error(s0 != cudaSuccess ? s0 : s1, "cudaStreamSynchronize(pipe_stream)");
+        return LDPC_ERR_CUDA;
+    }
     return launches;
 }
 

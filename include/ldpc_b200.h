@@ -113,11 +113,12 @@ typedef struct {
     uint64_t channel_seed;
     uint64_t channel_first_frame;
     const uint8_t *channel_codeword; /* device uint8 [N] broadcast to all frames, NULL = all-zero      */
-    /* Host path, layered int8, fp32 [N][F] input: with host_pack_threads >= 1 the library quantises each chunk
-     * to int8 (the kernel's own rule q = sat127(rint(y*llr_scale)), bit-identical results) on that many host
-     * threads into pinned staging buffers and copies a quarter of the bytes over PCIe; the quantisation of chunk
-     * k+1 runs under the copy and decode of chunk k.  0 = copy the fp32 values (the default; the choice for a
-     * busy host or when several ranks share few cores).                                                   */
+    /* Host path, layered int8, fp32 [N][F] input: the library can quantise each chunk to int8 on host threads (the
+     * kernel's own rule q = sat127(rint(y*llr_scale)), bit-identical results) into pinned staging buffers and copy a
+     * quarter of the bytes over PCIe; the quantisation of chunk k+1 runs under the copy and decode of chunk k.
+     * > 0: that many threads.  0 (default): automatic — the CPUs of the calling process' affinity mask (at most 32)
+     * when there are at least 12 of them, else a plain fp32 copy.  < 0: never (a busy host, or several ranks sharing
+     * few cores).                                                                                            */
     int host_pack_threads;
 } ldpc_decode_opts_t;
 

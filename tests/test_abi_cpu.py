@@ -89,3 +89,31 @@ def test_no_product_code_touches_the_oracle():
                              r"CDLL\([^)]*oracle", txt, flags=re.M):
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_host_quantiser_follows_the_kernel_rule():
+    """ldpcb_host_pack_nf (csrc/host_pack.cc, AVX-512 with non-temporal stores or scalar): q = sat127(rint(y * scale)),
+    ties to even, NaN -> 0 — the layered kernel's own load rule (bldpc_layered.cu `quant`), for ragged chunk widths,
+    unaligned outputs and any thread count."""
+    import ctypes as C
+    import cuda_ldpc_b200 as m
+    L = C.CDLL(m.lib_path)
+    L.ldpcb_host_pack_nf.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
+    L.ldpcb_host_pack_nf.restype = None
+    rng = np.random.default_rng(3)
+    N, F = 37, 1000
+    y = (rng.standard_normal((N, F)) * 6).astype(np.float32)
+    special = np.array([0.0625, -0.0625, 0.1875, -0.1875, 0.3125, 15.875, 15.9375, -15.9375, 1e9, -1e9, 1e-30, -1e-30,
+                        15.8125, -15.8125, 0.0, -0.0, np.nan, np.inf, -np.inf, 3.4e38, -3.4e38], np.float32)
+    y[0, : special.size] = special
+    y[5, 100: 100 + special.size] = special
+    for scale in (8.0, 1.0, 0.37):
+        with np.errstate(invalid="ignore", over="ignore"):
+            want = np.clip(np.rint(y * np.float32(scale)), -127, 127)
+        want = np.where(np.isnan(want), 0, want).astype(np.int8)
+        for f0, fc, threads in ((0, F, 1), (3, 333, 2), (64, 640, 5), (1, 65, 3), (500, 7, 1)):
+            buf = np.full(N * fc + 64, 77, np.int8)
+            for shift in (0, 1, 13):  # output alignment relative to 64 bytes
+                out = buf[shift: shift + N * fc]
+                L.ldpcb_host_pack_nf(y.ctypes.data, F, N, f0, fc, scale, out.ctypes.data, threads)
+                assert (out.reshape(N, fc) == want[:, f0: f0 + fc]).all(), (scale, f0, fc, threads, shift)
