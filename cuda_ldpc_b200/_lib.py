@@ -92,6 +92,8 @@ def _load():
                                         C.c_void_p, C.c_void_p]
     L.nb_ldpc_statistic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p]
+    L.nb_ldpc_encode_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    L.nb_ldpc_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 

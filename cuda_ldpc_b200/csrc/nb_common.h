@@ -25,4 +25,9 @@ struct nb_ldpc_code {
     float *d_cre, *d_cim;
     void *scratch;
     size_t scratch_bytes;
+    // encoder cache (host), built lazily by nb_ldpc_encode_info: information positions, pivot column per reduced row,
+    // and the dense map pivot symbol i = sum_j enc_P[i][j] * info symbol j
+    int enc_state;
+    std::vector<int> enc_info_pos, enc_piv_col;
+    std::vector<uint16_t> enc_P;
 };

@@ -52,6 +52,25 @@ class NbLdpcCode:
     def in_elems(self, in_kind):
         return {IN_SYMBOL_LLR: self.N * (self.q - 1), IN_BPSK: self.N * self.p, IN_QAM: self.N * 2}[in_kind]
 
+    def info_positions(self):
+        """positions of the K = N - rank(H) information symbols inside a codeword (nb_ldpc_encode_info)"""
+        k = C.c_int(0)
+        rc = lib.nb_ldpc_encode_info(self._h, C.byref(k), None)
+        if rc != 0:
+            raise LdpcError(rc, "nb_ldpc_encode_info")
+        pos = np.zeros(k.value, np.int32)
+        lib.nb_ldpc_encode_info(self._h, C.byref(k), pos.ctypes.data)
+        return pos
+
+    def encode(self, info_syms):
+        """info symbols [K] -> codeword [N] (uint16) with H c = 0; the reference has no encoder (codeword_test.h:1)."""
+        u = np.ascontiguousarray(info_syms, dtype=np.uint16)
+        cw = np.zeros(self.N, np.uint16)
+        rc = lib.nb_ldpc_encode(self._h, u.ctypes.data, cw.ctypes.data)
+        if rc != 0:
+            raise LdpcError(rc, "nb_ldpc_encode")
+        return cw
+
     def sigma(self, snrtype, snr_db, n_qam=0):
         """main.cu:221-228 (n_qam <= 0: the loaded constellation's size)."""
         return float(lib.nb_ldpc_sigma(self._h, int(snrtype), float(snr_db), int(n_qam)))

@@ -41,6 +41,7 @@ static void usage()
 }
 
 struct Gpu {
+    std::string err;  // ldpc_last_cuda_error() is per thread: captured inside the worker
     int dev;
     ldpc_code_t *code = nullptr;
     cudaStream_t st = nullptr;
@@ -161,13 +162,14 @@ int main(int argc, char **argv)
                         if (rc >= 0) rc = ldpc_statistic(x.code, x.out, LDPC_OUT_INT32_REF, nullptr, x.iters, a.batch, info.K, x.cw, x.cnt, x.st);
                     }
                     x.rc = rc;
+                    if (rc < 0) x.err = ldpc_last_cuda_error();
                 });
             }
             for (auto &t : th) t.join();
             next_frame += (unsigned long long)a.gpus * a.batch;
             memset(&tot, 0, sizeof(tot));
             for (auto &x : g) {
-                if (x.rc < 0) { fprintf(stderr, "ldpc_sim: gpu %d: %s %s\n", x.dev, ldpc_strerror(x.rc), ldpc_last_cuda_error()); return 1; }
+                if (x.rc < 0) { fprintf(stderr, "ldpc_sim: gpu %d: %s %s\n", x.dev, ldpc_strerror(x.rc), x.err.c_str()); return 1; }
                 cudaSetDevice(x.dev);
                 int64_t c[6];
                 cudaMemcpyAsync(c, x.cnt, sizeof c, cudaMemcpyDeviceToHost, x.st);

@@ -19,7 +19,8 @@
 #include "../../include/ldpc_b200.h"
 
 struct Args {
-    std::string matrix, gf, constellation, codeword;
+    std::string matrix, gf, constellation, codeword, results;
+    int encode = 0;
     int exp = 0, algo = NB_ALGO_EMS, nm = 2, nc = 2, maxit = 20, batch = 2048, gpus = 1, snrtype = 0;
     double snr_start = 0, snr_stop = 5, snr_step = 0.5;  // define.h:47-49
     long least_errors = 50, least_frames = 1000, max_frames = 0;
@@ -30,11 +31,17 @@ static void usage()
 {
     printf("usage: nb_ldpc_sim --matrix FILE --constellation FILE [--gf FILE] [--exp] [--algo ems|tmm|ltmm|fftbp|logqspa]\n"
            "       [--nm n --nc n] [--snr a b step] [--snrtype 0|1] [--maxit n] [--batch F] [--least-errors n]\n"
-           "       [--least-frames n] [--max-frames n] [--gpus g] [--seed s] [--codeword FILE]\n");
+           "       [--least-frames n] [--max-frames n] [--gpus g] [--seed s] [--codeword FILE | --encode]\n"
+           "       [--results FILE]\n"
+           "  --encode        transmit a random codeword (nb_ldpc_encode of random information symbols drawn from --seed)\n"
+           "                  instead of the all-zero word; the reference can only send zeros or its one hard-coded word\n"
+           "  --results FILE  append the reference's result row per finished SNR point (it always appends to results.txt,\n"
+           "                  myNBLDPC/src/Simulation.cpp:199-206)\n");
 }
 
 struct Gpu {
     int dev, rc = 0;
+    std::string err;  // ldpc_last_cuda_error() is per thread: captured inside the worker
     nb_ldpc_code_t *code = nullptr;
     cudaStream_t st = nullptr;
     float *x = nullptr;
@@ -54,6 +61,8 @@ int main(int argc, char **argv)
         else if (s == "--constellation") a.constellation = next(), i++;
         else if (s == "--codeword") a.codeword = next(), i++;
         else if (s == "--exp") a.exp = 1;
+        else if (s == "--encode") a.encode = 1;
+        else if (s == "--results") a.results = next(), i++;
         else if (s == "--algo") {
             std::string m = next(); i++;
             a.algo = m == "tmm" ? NB_ALGO_TMM : m == "ltmm" ? NB_ALGO_LAYERED_TMM : m == "fftbp" ? NB_ALGO_FFT_BP : NB_ALGO_EMS;
@@ -92,6 +101,19 @@ int main(int argc, char **argv)
             while ((int)cw.size() < info.N && fscanf(f, " %d%*[, \t\r\n]", &v) == 1) cw.push_back((uint16_t)v);
             fclose(f);
             if ((int)cw.size() != info.N) { fprintf(stderr, "nb_ldpc_sim: codeword file needs %d symbols\n", info.N); return 1; }
+        }
+        if (d == 0 && a.encode && cw.empty()) {  // random information symbols -> codeword (H c = 0 by construction)
+            int K = 0;
+            rc = nb_ldpc_encode_info(g[d].code, &K, nullptr);
+            std::vector<uint16_t> u(K > 0 ? K : 1);
+            unsigned long long s = a.seed * 6364136223846793005ull + 1442695040888963407ull;
+            for (int j = 0; j < K; j++) {
+                s = s * 6364136223846793005ull + 1442695040888963407ull;
+                u[j] = (uint16_t)((s >> 33) % (unsigned)info.q);
+            }
+            cw.assign(info.N, 0);
+            if (rc == LDPC_OK) rc = nb_ldpc_encode(g[d].code, u.data(), cw.data());
+            if (rc != LDPC_OK) { fprintf(stderr, "nb_ldpc_sim: encoder: %s\n", ldpc_strerror(rc)); return 1; }
         }
         const bool bpsk = info.n_const == 2;
         cudaStreamCreate(&g[d].st);
@@ -135,13 +157,14 @@ int main(int argc, char **argv)
                     if (rc >= 0) rc = nb_ldpc_decode_batch(x.code, x.x, x.out, a.maxit, &o);
                     if (rc >= 0) rc = nb_ldpc_statistic(x.code, x.out, x.iters, x.ok, a.batch, x.cw, x.cnt, x.st);
                     x.rc = rc;
+                    if (rc < 0) x.err = ldpc_last_cuda_error();
                 });
             }
             for (auto &t : th) t.join();
             next_frame += (unsigned long long)a.gpus * a.batch;
             memset(tot, 0, sizeof tot);
             for (auto &x : g) {
-                if (x.rc < 0) { fprintf(stderr, "nb_ldpc_sim: gpu %d: %s %s\n", x.dev, ldpc_strerror(x.rc), ldpc_last_cuda_error()); return 1; }
+                if (x.rc < 0) { fprintf(stderr, "nb_ldpc_sim: gpu %d: %s %s\n", x.dev, ldpc_strerror(x.rc), x.err.c_str()); return 1; }
                 cudaSetDevice(x.dev);
                 int64_t c[6];
                 cudaMemcpyAsync(c, x.cnt, sizeof c, cudaMemcpyDeviceToHost, x.st);
@@ -155,6 +178,15 @@ int main(int argc, char **argv)
         printf(" %.1f %8ld  %4ld  %6.4e  %6.4e  %.2f  %6.4esec  %9.3f\n", snr, (long)tot[0], (long)tot[1], tot[1] / nf,
                tot[2] / nf / info.N, tot[3] / nf, sec / nf, nf * kbits / sec / 1e6);
         fflush(stdout);
+        if (!a.results.empty()) {  // the reference's row, byte for byte its format (Simulation.cpp:198,205)
+            if (FILE *fp = fopen(a.results.c_str(), "a")) {
+                fprintf(fp, " %.1f %8ld  %4ld  %6.4e  %6.4e  %.2f  %6.4esec\n", snr, (long)tot[0], (long)tot[1], tot[1] / nf,
+                        tot[2] / nf / info.N, tot[3] / nf, sec / nf);
+                fclose(fp);
+            } else {
+                fprintf(stderr, "nb_ldpc_sim: can not open file: %s\n", a.results.c_str());
+            }
+        }
     }
     for (auto &x : g) {
         cudaSetDevice(x.dev);

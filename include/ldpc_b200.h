@@ -248,6 +248,14 @@ int nb_ldpc_statistic(const nb_ldpc_code_t *code, const uint16_t *hard_syms_dev,
                       const int *ok_dev, int batch, const uint16_t *codeword_syms_dev, int64_t *counters_dev,
                       void *stream);
 
+/* Systematic encoder over GF(q) for test vectors (the reference has none: its only non-zero codeword is the
+ * hard-coded CodeWord_sym_test of the BDS code, NB/include/codeword_test.h:1, NB/src/main.cu:190-212).  Gauss-Jordan
+ * elimination of H with the loaded tables, cached in the handle.  nb_ldpc_encode_info: *K = N - rank(H) information
+ * symbols and their positions in the codeword (ascending; the first K positions whenever the last M columns of H are
+ * invertible).  nb_ldpc_encode: info_syms uint16 [K] -> codeword_syms uint16 [N] with H c = 0 (host buffers).        */
+int nb_ldpc_encode_info(nb_ldpc_code_t *code, int *K, int *info_positions);
+int nb_ldpc_encode(nb_ldpc_code_t *code, const uint16_t *info_syms, uint16_t *codeword_syms);
+
 #ifdef __cplusplus
 }
 #endif
