@@ -33,6 +33,7 @@ static int ensure_device(const ldpc_code *cc)
     if (major != 10) return LDPC_ERR_NO_DEVICE;  // the library carries sm_100a code only
     LDPC_CUDA_TRY(cudaStreamCreateWithFlags(&c->pipe_stream[0], cudaStreamNonBlocking));
     LDPC_CUDA_TRY(cudaStreamCreateWithFlags(&c->pipe_stream[1], cudaStreamNonBlocking));
+    LDPC_CUDA_TRY(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
     c->device = dev;
     c->num_sms = sms;
     return LDPC_OK;
@@ -289,8 +290,49 @@ extern "C" size_t ldpc_out_bytes(const ldpc_code_t *c, int F, int fmt)
     }
 }
 
-extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *hard_bits, int iters,
+static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard_bits, int iters,
+                               const ldpc_decode_opts_t *o);
+
+// restores the caller's current device on every exit path
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int enter(int want)
+    {
+        LDPC_CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != want) {
+            LDPC_CUDA_TRY(cudaSetDevice(want));
+            switched = true;
+        }
+        return LDPC_OK;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) (void)cudaSetDevice(prev);
+    }
+};
+
+extern "C" int ldpc_decode_batch(const ldpc_code_t *cc, const void *llr, void *hard_bits, int iters,
                                  const ldpc_decode_opts_t *o)
+{
+    if (!cc || !hard_bits || !o || iters <= 0) return LDPC_ERR_ARG;
+    ldpc_code *c = const_cast<ldpc_code *>(cc);
+    // calls on one handle serialise (one scratch arena, common.h): host threads on call_mu, streams on last_use
+    std::lock_guard<std::mutex> lk(c->call_mu);
+    int rc = ensure_device(c);  // binds the handle to the device current at its first decode
+    if (rc != LDPC_OK) return rc;
+    DeviceGuard dg;             // later calls run on that device whatever the calling thread's current device is
+    rc = dg.enter(c->device);
+    if (rc != LDPC_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
+    if (c->last_use_valid) LDPC_CUDA_TRY(cudaStreamWaitEvent(st, c->last_use, 0));
+    rc = decode_batch_locked(c, llr, hard_bits, iters, o);
+    if (cudaEventRecord(c->last_use, st) == cudaSuccess) c->last_use_valid = true;
+    return rc;
+}
+
+static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard_bits, int iters,
+                               const ldpc_decode_opts_t *o)
 {
     if (!c || !hard_bits || !o || iters <= 0) return LDPC_ERR_ARG;
     const bool fused_channel = (o->llr_dtype == LDPC_DTYPE_CHANNEL);
@@ -343,7 +385,7 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         o_y = need;     need += need_conv ? align_up((size_t)c->N * F * 4) : 0;
         o_msgs = need;  need += align_up((size_t)c->M * c->dc_max * F * 4);
         o_hard = need;  need += align_up((size_t)c->N * F);
-        o_flags = need; need += align_up((size_t)(2 * F + 1) * 4);
+        o_flags = need; need += align_up((size_t)(2 * F + 2) * 4);
         o_app = need;   need += layered_f32 ? align_up((size_t)c->N * F * 4) : 0;
     }
     const size_t o_layer = need;  // the layered kernel sizes its own slice behind this offset
@@ -386,10 +428,10 @@ extern "C" int ldpc_decode_batch(const ldpc_code_t *c, const void *llr, void *ha
         unsigned char *hard = base + o_hard;
         if (layered_f32)
             rc = launch_layered_f32_nf(c, y, F, iters, o->early_exit, o->alpha, reinterpret_cast<float *>(base + o_app),
-                                       msgs, hard, d_it, d_ok, reinterpret_cast<int *>(base + o_flags), st, &launches);
+                                       msgs, hard, d_it, d_ok, reinterpret_cast<int *>(base + o_flags), st, &launches, host);
         else
             rc = launch_flooding_fp32(c, y, F, iters, o->early_exit, hard, d_it, d_ok, msgs,
-                                      reinterpret_cast<int *>(base + o_flags), st, &launches);
+                                      reinterpret_cast<int *>(base + o_flags), st, &launches, host);
         if (rc != LDPC_OK) return rc;
         if (layered_f32 && o->debug_app)
             LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_app, base + o_app, dbg_app_bytes,

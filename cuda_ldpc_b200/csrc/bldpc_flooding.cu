@@ -37,13 +37,15 @@ __device__ __forceinline__ void vset(float &v, int, float x) { v = x; }
 template <int VEC>
 __global__ void __launch_bounds__(256)
 flood_vn_kernel(const __grid_constant__ ColumnTables ct, float *__restrict__ msgs, const float *__restrict__ y,
-                unsigned char *__restrict__ hard, const int *__restrict__ done, int N, int Z, int F, int dcmax)
+                unsigned char *__restrict__ hard, const int *__restrict__ done, const int *__restrict__ stop, int N, int Z,
+                int F, int dcmax)
 {
     using V = typename Vec<VEC>::T;
     constexpr int kBatch = 4;
     const int FV = F / VEC;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)N * FV) return;
+    if (stop && *stop) return;  // genie stop reached in an earlier iteration: the batch is frozen (device-side exit)
     const int n = (int)(tid / FV);
     const int f = (int)(tid % FV) * VEC;
     const int c = n / Z, j = n - c * Z;
@@ -110,13 +112,15 @@ flood_vn_kernel(const __grid_constant__ ColumnTables ct, float *__restrict__ msg
 // 54 % of the HBM peak, 8 warps out of 9 waiting on the long scoreboard).
 template <int VEC>
 __global__ void __launch_bounds__(256)
-flood_cn_kernel(const __grid_constant__ LayerTables lt, float *__restrict__ msgs, int M, int Z, int F, int dcmax)
+flood_cn_kernel(const __grid_constant__ LayerTables lt, float *__restrict__ msgs, const int *__restrict__ stop, int M,
+                int Z, int F, int dcmax)
 {
     using V = typename Vec<VEC>::T;
     constexpr int kBatch = 8;
     const int FV = F / VEC;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)M * FV) return;
+    if (stop && *stop) return;
     const int m = (int)(tid / FV);
     const int f = (int)(tid % FV) * VEC;
     const int dc = lt.dc[m / Z];
@@ -199,10 +203,12 @@ genie_nf_kernel(const unsigned char *__restrict__ hard, int *__restrict__ bad, i
 // per-frame bookkeeping after iteration `it`; counter[0] += frames still running
 __global__ void
 flood_finalize_kernel(const int *__restrict__ bad, int *__restrict__ done, int *__restrict__ iters,
-                      int *__restrict__ ok, int *__restrict__ counter, int it, int F, int latch)
+                      int *__restrict__ ok, int *__restrict__ counter, const int *__restrict__ stop, int it, int F,
+                      int latch)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
+    if (stop && *stop) return;
     if (latch) {
         if (done[f]) return;
         iters[f] = it;
@@ -220,38 +226,49 @@ flood_finalize_kernel(const int *__restrict__ bad, int *__restrict__ done, int *
     }
 }
 
+// batch-wide stop (genie rule, B/LDPC_Decoder.cu:150-153: "all frames decoded" ends the loop): evaluated ON THE
+// DEVICE — later iterations are enqueued anyway and return at their first instruction, so ldpc_decode_batch with
+// device buffers never blocks the host (the reference copies N*F ints to the host and tests them there, every iteration)
+__global__ void flood_stop_kernel(const int *__restrict__ counter, int *__restrict__ stop)
+{
+    if (*counter == 0) *stop = 1;
+}
+
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 template <int VEC>
-static void launch_vn(const ldpc_code *c, float *msgs, const float *y, unsigned char *hard, const int *done, int F,
-                      cudaStream_t st)
+static void launch_vn(const ldpc_code *c, float *msgs, const float *y, unsigned char *hard, const int *done,
+                      const int *stop, int F, cudaStream_t st)
 {
     const long long n = (long long)c->N * (F / VEC);
-    flood_vn_kernel<VEC><<<blocks_for(n, 256), 256, 0, st>>>(c->ct, msgs, y, hard, done, c->N, c->Z, F, c->dc_max);
+    flood_vn_kernel<VEC><<<blocks_for(n, 256), 256, 0, st>>>(c->ct, msgs, y, hard, done, stop, c->N, c->Z, F, c->dc_max);
 }
 
 // y_nf: device fp32 [N][F]; hard_nf: device u8 [N][F]; iters_dev/ok_dev: device int [F];
-// msgs: device fp32 [M*dc_max][F]; flag_scratch: device int [2F + 1] (bad, done, counter).
+// msgs: device fp32 [M*dc_max][F]; flag_scratch: device int [2F + 2] (bad, done, counter, stop).
+// may_block: the caller synchronises anyway (host buffers), so the loop may read the 4-byte counter back and stop
+// enqueuing; otherwise (device buffers) every iteration is enqueued and the exit happens on the device.
 int launch_flooding_fp32(const ldpc_code *c, const float *y, int F, int iters, int exit_mode,
                          unsigned char *hard, int *iters_dev, int *ok_dev, float *msgs, int *flag_scratch,
-                         cudaStream_t st, int *launches)
+                         cudaStream_t st, int *launches, bool may_block)
 {
-    int *bad = flag_scratch, *done = flag_scratch + F, *counter = flag_scratch + 2 * F;
+    int *bad = flag_scratch, *done = flag_scratch + F, *counter = flag_scratch + 2 * F, *stop = counter + 1;
     const size_t msg_bytes = (size_t)c->M * c->dc_max * F * sizeof(float);
     LDPC_CUDA_TRY(cudaMemsetAsync(msgs, 0, msg_bytes, st));  // B/LDPC_Decoder.cu:82
-    LDPC_CUDA_TRY(cudaMemsetAsync(flag_scratch, 0, (size_t)(2 * F + 1) * sizeof(int), st));
+    LDPC_CUDA_TRY(cudaMemsetAsync(flag_scratch, 0, (size_t)(2 * F + 2) * sizeof(int), st));
     const bool vec4 = (F % 4 == 0);
     const int latch = (exit_mode == LDPC_EXIT_SYNDROME);
+    const int *gstop = (exit_mode == LDPC_EXIT_GENIE) ? stop : nullptr;  // syndrome mode freezes frames one by one (done[])
     int n = 0, it = 0;
     while (it < iters) {
         it++;
         if (vec4) {
-            launch_vn<4>(c, msgs, y, hard, latch ? done : nullptr, F, st);
-            flood_cn_kernel<4><<<blocks_for((long long)c->M * (F / 4), 256), 256, 0, st>>>(c->lt, msgs, c->M, c->Z,
-                                                                                          F, c->dc_max);
+            launch_vn<4>(c, msgs, y, hard, latch ? done : nullptr, gstop, F, st);
+            flood_cn_kernel<4><<<blocks_for((long long)c->M * (F / 4), 256), 256, 0, st>>>(c->lt, msgs, gstop, c->M,
+                                                                                          c->Z, F, c->dc_max);
         } else {
-            launch_vn<1>(c, msgs, y, hard, latch ? done : nullptr, F, st);
-            flood_cn_kernel<1><<<blocks_for((long long)c->M * F, 256), 256, 0, st>>>(c->lt, msgs, c->M, c->Z, F,
+            launch_vn<1>(c, msgs, y, hard, latch ? done : nullptr, gstop, F, st);
+            flood_cn_kernel<1><<<blocks_for((long long)c->M * F, 256), 256, 0, st>>>(c->lt, msgs, gstop, c->M, c->Z, F,
                                                                                     c->dc_max);
         }
         n += 2;
@@ -264,10 +281,14 @@ int launch_flooding_fp32(const ldpc_code *c, const float *y, int F, int iters, i
             else
                 syndrome_nf_kernel<<<blocks_for((long long)c->M * F, 256), 256, 0, st>>>(c->lt, hard, bad, c->M,
                                                                                         c->Z, F);
-            flood_finalize_kernel<<<blocks_for(F, 256), 256, 0, st>>>(bad, done, iters_dev, ok_dev, counter, it, F,
+            flood_finalize_kernel<<<blocks_for(F, 256), 256, 0, st>>>(bad, done, iters_dev, ok_dev, counter, gstop, it, F,
                                                                      latch);
             n += 2;
-            if (exit_mode != LDPC_EXIT_NONE && !last) {
+            if (gstop && !last) {
+                flood_stop_kernel<<<1, 1, 0, st>>>(counter, stop);
+                n++;
+            }
+            if (may_block && exit_mode != LDPC_EXIT_NONE && !last) {
                 int running = 0;  // the reference copies N*F ints per iteration here (:135); we copy 4 bytes
                 LDPC_CUDA_TRY(cudaMemcpyAsync(&running, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
                 LDPC_CUDA_TRY(cudaStreamSynchronize(st));

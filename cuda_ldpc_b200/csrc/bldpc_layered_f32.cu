@@ -131,17 +131,18 @@ hard_from_app_kernel(const float *__restrict__ app, unsigned char *__restrict__ 
 __global__ void syndrome_nf_kernel(const __grid_constant__ LayerTables lt, const unsigned char *__restrict__ hard,
                                    int *__restrict__ bad, int M, int Z, int F);
 __global__ void flood_finalize_kernel(const int *__restrict__ bad, int *__restrict__ done, int *__restrict__ iters,
-                                      int *__restrict__ ok, int *__restrict__ counter, int it, int F, int latch);
+                                      int *__restrict__ ok, int *__restrict__ counter, const int *__restrict__ stop, int it,
+                                      int F, int latch);
 
 // y: device fp32 [N][F]; app: device fp32 [N][F] scratch (also the debug dump); msgs: [M*dc_max][F]
 int launch_layered_f32_nf(const ldpc_code *c, const float *y, int F, int iters, int exit_mode, float alpha, float *app,
                           float *msgs, unsigned char *hard, int *iters_dev, int *ok_dev, int *flag_scratch,
-                          cudaStream_t st, int *launches)
+                          cudaStream_t st, int *launches, bool may_block)
 {
     int *bad = flag_scratch, *done = flag_scratch + F, *counter = flag_scratch + 2 * F;
     LDPC_CUDA_TRY(cudaMemcpyAsync(app, y, (size_t)c->N * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
     LDPC_CUDA_TRY(cudaMemsetAsync(msgs, 0, (size_t)c->M * c->dc_max * F * sizeof(float), st));
-    LDPC_CUDA_TRY(cudaMemsetAsync(flag_scratch, 0, (size_t)(2 * F + 1) * sizeof(int), st));
+    LDPC_CUDA_TRY(cudaMemsetAsync(flag_scratch, 0, (size_t)(2 * F + 2) * sizeof(int), st));
     const bool vec4 = (F % 4 == 0);
     const int latch = (exit_mode == LDPC_EXIT_SYNDROME);
     const long long nt = (long long)c->Z * (vec4 ? F / 4 : F), nf = (long long)c->N * F;
@@ -163,9 +164,11 @@ int launch_layered_f32_nf(const ldpc_code *c, const float *y, int F, int iters, 
             LDPC_CUDA_TRY(cudaMemsetAsync(bad, 0, (size_t)F * sizeof(int), st));
             LDPC_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), st));
             syndrome_nf_kernel<<<(unsigned)(((long long)c->M * F + 255) / 256), 256, 0, st>>>(c->lt, hard, bad, c->M, c->Z, F);
-            flood_finalize_kernel<<<(F + 255) / 256, 256, 0, st>>>(bad, done, iters_dev, ok_dev, counter, it, F, latch);
+            flood_finalize_kernel<<<(F + 255) / 256, 256, 0, st>>>(bad, done, iters_dev, ok_dev, counter, nullptr, it, F, latch);
             n += 3;
-            if (latch && !last) {
+            // device buffers: never block — converged frames are frozen one by one through done[], the remaining
+            // iterations run as no-ops; host buffers: the caller synchronises anyway, so stop enqueuing early
+            if (may_block && latch && !last) {
                 int running = 0;
                 LDPC_CUDA_TRY(cudaMemcpyAsync(&running, counter, sizeof(int), cudaMemcpyDeviceToHost, st));
                 LDPC_CUDA_TRY(cudaStreamSynchronize(st));

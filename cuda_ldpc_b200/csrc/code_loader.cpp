@@ -128,6 +128,8 @@ extern "C" int ldpc_load_code(const char *path, int J, int L, int Z, ldpc_code_t
     c->pack_host[0] = c->pack_host[1] = nullptr;
     c->pack_host_bytes = 0;
     c->pack_ev[0] = c->pack_ev[1] = nullptr;
+    c->last_use = nullptr;
+    c->last_use_valid = false;
     c->enc_state = 0;
     memset(&c->lt, 0, sizeof(c->lt));
     memset(&c->ct, 0, sizeof(c->ct));
@@ -190,6 +192,7 @@ extern "C" int ldpc_load_code(const char *path, int J, int L, int Z, ldpc_code_t
 extern "C" void ldpc_free_code(ldpc_code_t *code)
 {
     if (!code) return;
+    if (code->last_use) cudaEventDestroy(code->last_use);
     if (code->scratch) cudaFree(code->scratch);
     for (int i = 0; i < 2; i++) {
         if (code->pipe_stream[i]) cudaStreamDestroy(code->pipe_stream[i]);

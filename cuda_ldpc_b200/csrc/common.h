@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -58,7 +59,14 @@ struct ldpc_code {
     ldpcb::ColumnTables ct;
     int device;
     int num_sms;
-    // scratch arena (device), grown on demand under `mu`
+    // One scratch arena per handle: calls on one handle SERIALISE.  `call_mu` is held for the whole of every decode
+    // call (host threads), and `last_use` (recorded on the call's stream when it returns) is waited for by the next
+    // call's stream, so work enqueued on different streams never shares the arena in time.  Concurrency = one handle
+    // per stream / host thread (a handle is a few KB of tables plus its arena).
+    std::mutex call_mu;
+    cudaEvent_t last_use;
+    bool last_use_valid;
+    // scratch arena (device), grown on demand
     void *scratch;
     size_t scratch_bytes;
     // two internal streams for the chunked host path (H2D of chunk k+1 under the decode of chunk k)
@@ -80,7 +88,7 @@ int ensure_scratch(const ldpc_code *code, size_t bytes, void **out);
 
 int launch_flooding_fp32(const ldpc_code *code, const float *y_nf, int F, int iters, int exit_mode,
                          unsigned char *hard_nf, int *iters_dev, int *ok_dev, float *msgs, int *flag_scratch,
-                         cudaStream_t st, int *launches);
+                         cudaStream_t st, int *launches, bool may_block);
 
 struct LayeredArgs {
     const void *llr;
@@ -103,5 +111,5 @@ int layered_i8_scratch_bytes(const ldpc_code *code, int F, int beta_num, size_t 
 int launch_layered_i8(const ldpc_code *code, const LayeredArgs &a, cudaStream_t st, int *launches);
 int launch_layered_f32_nf(const ldpc_code *code, const float *y_nf, int F, int iters, int exit_mode, float alpha,
                           float *app, float *msgs, unsigned char *hard_nf, int *iters_dev, int *ok_dev,
-                          int *flag_scratch, cudaStream_t st, int *launches);
+                          int *flag_scratch, cudaStream_t st, int *launches, bool may_block);
 }  // namespace ldpcb

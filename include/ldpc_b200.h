@@ -43,8 +43,10 @@ typedef struct ldpc_code ldpc_code_t;
  * reference's text format (whitespace/CRLF tolerant).  J, L, Z <= 0: parsed from
  * "J<j>_L<l>_Z<z>" in the file name; PON_LDPC.txt needs 12/69/256 explicitly.
  * The graph is the true circulant row = (col - s) mod Z (the reference's Transform_H mis-wires
- * it).  The handle owns device-resident tables and a scratch arena; it is immutable
- * after load, so decode calls with distinct streams may run concurrently.                 */
+ * it).  The handle owns its tables and ONE scratch arena, bound to the device that is current at its
+ * first decode call (later calls switch to that device and back).  Calls on one handle are safe from any host
+ * thread and any stream but SERIALISE (a per-handle lock for the call, an event chain between the streams); for
+ * concurrent decoding load one handle per stream or host thread — a handle is a few KB of tables plus its arena.  */
 int ldpc_load_code(const char *blockh_path, int J, int L, int Z, ldpc_code_t **out);
 void ldpc_free_code(ldpc_code_t *code);
 
@@ -126,8 +128,11 @@ void ldpc_decode_opts_default(ldpc_decode_opts_t *opts);
 
 /* Replaces LDPC_Decoder_GPU (B/LDPC_Decoder.cuh:5, called from B/Simulation.cu:143).
  * llr: channel values (the reference feeds the raw sample y = 1-2c+sigma*n, B/LDPC_Encoder.cu:38).
- * With mem_space = HOST the call copies in/out and synchronises; with DEVICE it only enqueues
- * work on opts->stream.  Returns the number of kernel launches enqueued (>= 0) or an error.  */
+ * With mem_space = HOST the call copies in/out and synchronises; with DEVICE it only enqueues work on
+ * opts->stream and never waits for the device — early-exit modes terminate on the device (layered int8: inside the
+ * kernel; flooding / layered fp32: the remaining iterations are enqueued and return at their first instruction once
+ * the stop condition holds), except when the scratch arena has to grow (first call, or a larger batch).
+ * Returns the number of kernel launches enqueued (>= 0) or an error.                          */
 int ldpc_decode_batch(const ldpc_code_t *code, const void *llr, void *hard_bits, int iters,
                       const ldpc_decode_opts_t *opts);
 

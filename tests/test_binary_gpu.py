@@ -263,10 +263,10 @@ def test_chunked_host_path_equals_device_path(oracle, layout, fmt):
     got = rd.D.cpu().numpy()
     assert (rh.D == (got.view(np.uint32) if fmt == m.OUT_BITPACK else got)).all()
     assert (rh.iters == rd.iters.cpu().numpy()).all() and (rh.ok == rd.ok.cpu().numpy()).all()
-    assert rh.launches == 3 and rd.launches == 1
+    assert rh.launches >= 3 and rd.launches == 1  # 3 equal chunks, or 4 in the hybrid pack / copy feed
     # host pack: the chunks quantised to int8 on host threads before the copy — same result bit for bit
     rp = code.decode(yy, 10, host_pack_threads=3, **kw)
-    assert (rp.D == rh.D).all() and (rp.iters == rh.iters).all() and (rp.ok == rh.ok).all() and rp.launches == 3
+    assert (rp.D == rh.D).all() and (rp.iters == rh.iters).all() and (rp.ok == rh.ok).all() and rp.launches >= 3
 
 
 def test_host_pack_extreme_values(oracle):
@@ -374,3 +374,65 @@ def test_full_size_roundtrip_properties(oracle):
     assert (rp.D == r.D[:, perm]).all() and (rp.iters == r.iters[perm]).all()
     rf = code.decode_channel(F, 10, sigma, seed=5, first_frame=0, codeword=cwd, **kw)
     assert (rf.D == r.D).all() and (rf.iters == r.iters).all() and (rf.ok == r.ok).all()
+
+
+@pytest.mark.parametrize("mode", [m.EXIT_GENIE, m.EXIT_SYNDROME])
+def test_flooding_device_path_exits_on_the_device(oracle, mode):
+    """With device buffers ldpc_decode_batch only enqueues: the genie / syndrome stop is evaluated on the device
+    (remaining iterations return at their first instruction).  Same bits, flags, iteration counts and messages as the
+    host-buffer call (which may stop enqueuing early) and as the oracle."""
+    import torch
+    code, oc = load(oracle, "C1")
+    y = noisy(oracle, code.N, 48, 4.2)   # every frame converges well before maxIT = 30
+    rh = code.decode(y, 30, early_exit=mode, debug=True)
+    rd = code.decode(torch.as_tensor(y, device="cuda"), 30, early_exit=mode, debug=True)
+    torch.cuda.synchronize()
+    D, it, rq = orc_flood(oracle, oc, y, 30, mode)
+    assert it.max() < 30
+    assert (rd.D.cpu().numpy() == D).all() and (rd.iters.cpu().numpy() == it).all()
+    assert (rh.D == D).all() and (rh.iters == it).all()
+    if mode == m.EXIT_GENIE:  # the whole batch freezes at the stop (syndrome mode freezes the decisions frame by frame,
+        # the check-node pass of already latched frames keeps running in both paths)
+        assert (rd.msgs.cpu().numpy().view(np.uint32) == rh.msgs.view(np.uint32)).all()
+        assert (rd.msgs.cpu().numpy().view(np.uint32) == rq.view(np.uint32)).all()
+    assert rd.launches > rh.launches   # the device path enqueued all 30 iterations, the host path stopped early
+    for alpha in (1.0,):
+        lh = code.decode(y, 30, schedule=m.SCHED_LAYERED, msg_dtype=m.DTYPE_FP32, early_exit=m.EXIT_SYNDROME, debug=True)
+        ld = code.decode(torch.as_tensor(y, device="cuda"), 30, schedule=m.SCHED_LAYERED, msg_dtype=m.DTYPE_FP32,
+                         early_exit=m.EXIT_SYNDROME, debug=True)
+        torch.cuda.synchronize()
+        assert (ld.D.cpu().numpy() == lh.D).all() and (ld.iters.cpu().numpy() == lh.iters).all()
+        assert (ld.app.cpu().numpy().view(np.uint32) == lh.app.view(np.uint32)).all()
+
+
+def test_one_handle_from_two_threads_and_streams(oracle):
+    """include/ldpc_b200.h: calls on one handle are safe from any host thread / stream and serialise on its scratch
+    arena.  Two threads hammer the same handle on their own streams; every result equals the single-threaded one."""
+    import threading
+    import torch
+    code, _ = load(oracle, "C3")
+    ys = [torch.as_tensor(noisy(oracle, code.N, 64, 3.2, seed=100 + i), device="cuda") for i in range(2)]
+    kw = dict(schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=m.OUT_U8, msg_max=31)
+    want = []
+    for y in ys:
+        r = code.decode(y, 10, **kw)
+        torch.cuda.synchronize()
+        want.append((r.D.clone(), r.iters.clone()))
+    errs = []
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream()
+            for _ in range(40):
+                r = code.decode(ys[i], 10, stream=st.cuda_stream, **kw)
+                st.synchronize()
+                if not ((r.D == want[i][0]).all().item() and (r.iters == want[i][1]).all().item()):
+                    errs.append(f"thread {i}: result differs")
+                    return
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
