@@ -355,3 +355,51 @@ def test_large_batch_properties(meta, name, exp, snr, algo):
     o_a, i_a, _ = code.decode(x[:h].contiguous(), 20, algo=a, in_kind=kind, sigma=sigma)
     o_b, i_b, _ = code.decode(x[h:].contiguous(), 20, algo=a, in_kind=kind, sigma=sigma)
     assert torch.equal(torch.cat([o_a, o_b]), out) and torch.equal(torch.cat([i_a, i_b]), it)
+
+
+@pytest.mark.parametrize("name,exp,snr,F", [("C4", 1, 12.5, 24), ("C5", 1, 5.0, 16)])
+def test_encoded_codewords_through_channel_and_decoder(nb_oracle, gf_dir, meta, name, exp, snr, F):
+    """nb_ldpc_encode -> oracle Modulate + AWGNChannel_CPU (NB/src/LDPC_Encoder.cpp:18-68) -> fused demapper + TMM /
+    layered TMM on the GPU == the oracle's decoder on the same samples, for a RANDOM codeword (the reference can only
+    send zeros for these matrices); converged frames return exactly the transmitted codeword; and the device
+    transmitter (nb_ldpc_modulate_awgn with a codeword) + nb_ldpc_statistic count zero errors at high SNR."""
+    import torch
+    cfg = meta["configs"][name]
+    mt, gf, cs = paths(cfg, gf_dir)
+    h = orc_load(nb_oracle, cfg, gf_dir, exp)
+    code = m.NbLdpcCode(mt, None, cs, coef_is_exponent=bool(exp))
+    N, q, p = code.N, code.q, code.p
+    pos = code.info_positions()
+    cw = code.encode(np.random.default_rng(5).integers(0, q, len(pos)).astype(np.uint16))
+    sym = cw.astype(np.int32)
+    assert nb_oracle.nb_orc_syndrome_ok(h, sym.ctypes.data) == 1
+    L = N * p if cfg["n_qam"] == 2 else N
+    tx = np.zeros(2 * L, np.float32)
+    nb_oracle.nb_orc_modulate(h, sym.ctypes.data, tx.ctypes.data)
+    sigma = nb_oracle.nb_orc_sigma(h, 0, snr)
+    seed = np.array([173, 173, 173], np.int32)
+    lch = np.zeros((F, N * (q - 1)), np.float32)
+    rxs = np.zeros((F, 2 * L), np.float32)
+    for f in range(F):
+        nb_oracle.nb_orc_awgn(seed.ctypes.data, sigma, tx.ctypes.data, rxs[f].ctypes.data, L)
+        nb_oracle.nb_orc_demodulate(h, sigma, rxs[f].ctypes.data, lch[f].ctypes.data)
+    inp, kind = channel_input(cfg, rxs, N, p)
+    for a in (m.ALGO_TMM, m.ALGO_LAYERED_TMM):
+        o_out = np.zeros((F, N), np.int32); o_it = np.zeros(F, np.int32); o_ok = np.zeros(F, np.int32)
+        nb_oracle.nb_orc_decode_batch(h, a, 0, lch.ctypes.data, F, 20, 2, 2, o_out.ctypes.data, o_it.ctypes.data,
+                                      o_ok.ctypes.data)
+        out, it, ok = code.decode(inp, 20, algo=a, in_kind=kind, sigma=sigma)
+        assert (ok == o_ok).all() and (it == o_it).all() and (out.astype(np.int32) == o_out).all(), (name, a)
+        assert o_ok.sum() >= F // 2 and (out[ok == 1] == cw[None, :]).all()
+    # device transmitter with the codeword, far above the waterfall: every frame decodes to it, the counters say so
+    cwd = torch.as_tensor(cw.astype(np.int16), device="cuda")
+    hi_sigma = code.sigma(0, snr + 6.0)
+    x = code.modulate_awgn(2048, hi_sigma, seed=3, codeword=cwd)
+    out, it, ok = code.decode(x.view(2048, -1), 20, algo=m.ALGO_LAYERED_TMM, in_kind=kind, sigma=hi_sigma)
+    torch.cuda.synchronize()
+    assert (out.view(torch.int16) == cwd[None, :]).all() and ok.all()
+    cnt = torch.zeros(6, dtype=torch.int64, device="cuda")
+    assert m.lib.nb_ldpc_statistic(code._h, out.data_ptr(), it.data_ptr(), ok.data_ptr(), 2048, cwd.data_ptr(),
+                                   cnt.data_ptr(), torch.cuda.current_stream().cuda_stream) >= 0
+    c = cnt.cpu().numpy()
+    assert c[0] == 2048 and c[1] == 0 and c[2] == 0
