@@ -383,9 +383,10 @@ def run_ours(args):
     hk = torch.empty(Fe, dtype=torch.int32).pin_memory().numpy()
     hkw = dict(kw, out=ho, iters_out=hi, ok_out=hk)
     cpus = len(os.sched_getaffinity(0))
-    # host quantiser threads: the library's automatic choice when this process has the host to itself; an explicit
-    # share of the cores when several ranks run on one box (< 8 per rank: plain fp32 copy)
-    pack = 0 if world == 1 else ((os.cpu_count() or 1) // world if (os.cpu_count() or 1) // world >= 8 else -1)
+    # host quantiser: the library's automatic choice when this process has the host to itself.  With several ranks on
+    # one box the host's DRAM is the shared resource and a plain fp32 DMA copy costs it one read per byte where the
+    # quantiser costs a read, a write and the DMA's read (measured at N = 2: 10.3 vs 12.0 Gbit/s): off.
+    pack = 0 if world == 1 else -1
 
     def host_parity():
         return bool((torch.from_numpy(ho).to(dev) == dev_res[0]).all().item() and
