@@ -9,11 +9,13 @@
 //    HADD2 / HFMA2 / HSET2 / PRMT / LOP3 plus the 16x2 integer min/max family on fp16 bit patterns
 //    (VIMNMX.U16x2, VIMNMX3.U16x2, VIADDMNMX.S16x2.RELU) — sm_100a has no native 8x4 SIMD integer
 //    min/compare (the __v*4 intrinsics expand to 5-10 instructions, profiles/r01_simd_sass.txt);
-//  * the compressed check record {min1, min2, idx, sign bits} is streamed through a per-CTA
-//    slice of a scratch buffer (L2 evict-last; for J15_L30_Z1280 the 148 x 19200 x 32 B = 91 MB do
-//    not stay in L2 beside the streaming input, about half of the record reads come from HBM —
-//    ~2 MB of DRAM traffic per frame, a quarter of the HBM peak); each thread loads the record of
-//    its NEXT row into registers while it finishes the current one, which hides that latency;
+//  * the check-to-variable messages are one byte (c2v + 127) per edge and codeword = one 32-bit word per
+//    edge and group, 256-bit blocks per check row in a per-CTA slice of a scratch buffer (L2 evict-last;
+//    for J15_L30_Z1280 the 148 x 19200 x 32 B = 91 MB do not stay in L2 beside the streaming input, about
+//    half of the reads come from HBM — ~2 MB of DRAM traffic per frame, 30 % of the HBM peak); each thread
+//    loads the block of its NEXT row into registers while it finishes the current one (dc <= 12), which
+//    hides that latency.  Round 1 stored compressed records {min1, min2, idx, sign bits} instead and paid
+//    five instructions per edge to rebuild every old message (process_row_x's comment);
 //  * the syndrome (early exit / ok flag) is a cheap extra pass: XOR of the sign bits.
 //
 // Update rules: exactly oracle/bldpc_oracle.c "int8 layered rules" (t = APP - c2v_old,
@@ -26,31 +28,11 @@
 #include "philox.cuh"
 #include "stress.cuh"
 
-// Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it):
-//   LDPC_REC_PRELOAD   2  the record of a thread's next step is loaded into registers right after the edge loop
-//                         of the current row (1 = after the record store): 9.07 -> 8.70 -> 8.45 ms; an L1 or L2
-//                         prefetch on top of it LOSES 2 %
-//   LDPC_REC_PREFETCH  0  1 = prefetch.global.L1, 2 = prefetch.global.L2 of the next step's record at row start
-//   LDPC_PARITY_XOR    1  sign parity as xor of the t patterns (LOP3) instead of an fp16 count (9.30 -> 9.06 ms)
-//   LDPC_NEG_ALU       1  (t < 0) as HSET2 on the ALU pipe instead of fma.sat on the FMA pipe: after the rework the
-//                         fp16 FMA pipe is the fuller one (8.76 -> 8.63 ms); moving the sign shifts to the ALU pipe
-//                         (SHF instead of IMAD.SHL) or phase 2's sign product to the FMA pipe both LOSE
+// Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it; DESIGN.md §9):
 //   LDPC_LOAD_DEPTH    8  channel-value vectors in flight per thread in the load phase
-//   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values (on: evicts records, +4 %)
+//   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values (on: evicts messages, +4 %)
 #ifndef LDPC_L2_PREFETCH
 #define LDPC_L2_PREFETCH 0
-#endif
-#ifndef LDPC_REC_PREFETCH
-#define LDPC_REC_PREFETCH 0
-#endif
-#ifndef LDPC_PARITY_XOR
-#define LDPC_PARITY_XOR 1
-#endif
-#ifndef LDPC_REC_PRELOAD
-#define LDPC_REC_PRELOAD 2
-#endif
-#ifndef LDPC_NEG_ALU
-#define LDPC_NEG_ALU 1
 #endif
 //   LDPC_HI_PRELOAD    0  degree buckets above 12 load a row's old messages at the start of the row instead of one
 //                         step ahead: 16-32 fewer live registers in phase 2 (B200, PON: 39.4 -> 41.6 Gbit/s)
