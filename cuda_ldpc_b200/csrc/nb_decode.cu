@@ -505,18 +505,48 @@ struct TmmShared {
     float *vv, *dU, *Min1, *Min2, *I, *Ev;  // per group: [dc_max*q], [dc_max*q], [q] x4
     int2 *MC;                               // [q] {Min1 bits, MinCol}
     int *MinCol, *Path, *Zn;                // [q], [2q], [dc_max + 1] (last = syndrome)
+    int *tvn, *tgf, *tinv;                  // [dc_max] x3: the row's edge table (variable, coefficient, its inverse)
+    float *mn;                              // [dc_max] minimum of every edge's v2c vector
 };
+__host__ __device__ constexpr size_t tmm_group_floats(int q, int dc_max)
+{
+    return ((size_t)2 * dc_max * q + 9 * q + dc_max + 1 + 4 * dc_max + 3) & ~(size_t)3;
+}
 
 // the q threads of a group process check `row`; a = thread's symbol index.  Every thread of the CTA
 // calls this (same barriers); threads with act == false touch no memory.
-__device__ void tmm_check(const NbParams &p, int row, int a, bool act, const TmmShared &s, float *LLR, float *c2v,
-                          bool write_llr)
+//
+// Latency (ncu, profiles/r02_ncu_nb_*.txt: long-scoreboard stalls 3-4 warps per issue cycle): the frame state
+// lives in an L2-resident slot, so every dependent global load costs ~300 cycles.  The row's edge table
+// (variable, coefficient, inverse coefficient — read again in every phase below) is therefore staged in
+// shared memory once per row, and the LLR / c2v vectors of the row's edges are loaded four edges at a time
+// before the first of them is used (a loop of dependent load -> subtract -> store pairs serialised them): layered TMM
+// C5 126 -> 140, BDS 159 -> 170, C4 660 -> 688 info Mbit/s.  An L1 prefetch of the next row's vectors on top LOSES 4 %.
+__device__ void tmm_check(const NbParams &p, int row, int nrow, int a, bool act, const TmmShared &s, float *LLR,
+                          float *c2v, bool write_llr)
 {
     const int q = p.q, w = act ? p.cw[row] : 0;
+    if (act)
+        for (int d = a; d < w; d += q) {
+            const int h = p.c_gf[row * p.dc_max + d];
+            s.tvn[d] = p.c_vn[row * p.dc_max + d];
+            s.tgf[d] = h;
+            s.tinv[d] = __ldg(p.inv + h);
+        }
+    cta_sync();
     // v2c = LLR - c2v (:472-475 / :644)
-    for (int d = 0; d < w; d++) {
-        const int vn = p.c_vn[row * p.dc_max + d];
-        s.vv[d * q + a] = __fsub_rn(LLR[vn * q + a], c2v[((size_t)row * p.dc_max + d) * q + a]);
+    constexpr int kBatch = 4;
+    for (int d0 = 0; d0 < w; d0 += kBatch) {
+        float l[kBatch], c[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; u++) {
+            const int d = min(d0 + u, w - 1);  // tail: re-read the last edge instead of predicating
+            l[u] = LLR[s.tvn[d] * q + a];
+            c[u] = c2v[((size_t)row * p.dc_max + d) * q + a];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; u++)
+            if (d0 + u < w) s.vv[(d0 + u) * q + a] = __fsub_rn(l[u], c[u]);
     }
     cta_sync();
     // d_TMM_Get_Zn :704-723: hard symbol of every edge = first minimum of its v2c vector.  q >= 32: one warp of
@@ -539,19 +569,23 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
                     mx = ox;
                 }
             }
-            if (lane == 0) s.Zn[d] = gmul(p, mx, p.c_gf[row * p.dc_max + d]);
+            if (lane == 0) {
+                s.Zn[d] = gmul(p, mx, s.tgf[d]);
+                s.mn[d] = mn;
+            }
         }
     } else {
         for (int d = a; d < w; d += q) {
             float mn = INFINITY;
             int me = 0;
-            const int h = p.c_gf[row * p.dc_max + d];
+            const int h = s.tgf[d];
             for (int x = 0; x < q; x++)
                 if (s.vv[d * q + x] < mn) {
                     mn = s.vv[d * q + x];
                     me = gmul(p, x, h);
                 }
             s.Zn[d] = me;
+            s.mn[d] = mn;
         }
     }
     cta_sync();
@@ -560,11 +594,8 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
         for (int d = 0; d < w; d++) syn ^= s.Zn[d];
         s.Zn[p.dc_max] = syn;
     }
-    for (int d = 0; d < w; d++) {  // d_TMM_Get_deltaU :725-743
-        const int hinv = __ldg(p.inv + p.c_gf[row * p.dc_max + d]);
-        const float mn = s.vv[d * q + gmul(p, hinv, s.Zn[d])];
-        s.dU[d * q + (a ^ s.Zn[d])] = __fsub_rn(s.vv[d * q + gmul(p, hinv, a)], mn);
-    }
+    for (int d = 0; d < w; d++)  // d_TMM_Get_deltaU :725-743; vv[h^-1 Zn] is the minimum found above
+        s.dU[d * q + (a ^ s.Zn[d])] = __fsub_rn(s.vv[d * q + gmul(p, s.tinv[d], a)], s.mn[d]);
     cta_sync();
     if (act) {  // TMM_Get_Min :745-770
         float m1 = INFINITY, m2 = INFINITY;
@@ -622,14 +653,11 @@ __device__ void tmm_check(const NbParams &p, int row, int a, bool act, const Tmm
     const int syn = act ? s.Zn[p.dc_max] : 0;
     for (int d = 0; d < w; d++) {  // :496-521, thread = eta
         const float l = (a == 0) ? 0.0f : ((d != s.Path[2 * a] && d != s.Path[2 * a + 1]) ? s.I[a] : s.Ev[a]);
-        const int hinv = __ldg(p.inv + p.c_gf[row * p.dc_max + d]);
-        const int beta = gmul(p, hinv, a ^ syn ^ s.Zn[d]);
+        const int beta = gmul(p, s.tinv[d], a ^ syn ^ s.Zn[d]);
         const float m = (float)((double)l * 0.8);
         c2v[((size_t)row * p.dc_max + d) * q + beta] = m;
-        if (write_llr) {  // layered: LLR = v2c + c2v_new (:684-689)
-            const int vn = p.c_vn[row * p.dc_max + d];
-            LLR[vn * q + beta] = __fadd_rn(s.vv[d * q + beta], m);
-        }
+        if (write_llr)  // layered: LLR = v2c + c2v_new (:684-689)
+            LLR[s.tvn[d] * q + beta] = __fadd_rn(s.vv[d * q + beta], m);
     }
     cta_sync();
 }
@@ -650,7 +678,7 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
     // thread groups of q threads: one check per group (layered: a single group keeps the row order)
     const int groups = layered ? 1 : max(1, T / q);
     const int g = tid / q, a = tid - g * q;
-    const size_t per_group = ((size_t)2 * p.dc_max * q + 9 * q + p.dc_max + 1 + 3) & ~(size_t)3;
+    const size_t per_group = tmm_group_floats(q, p.dc_max);
     TmmShared s;
     {
         float *base = smem + (size_t)(g < groups ? g : 0) * per_group;
@@ -664,6 +692,10 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
         s.MinCol = reinterpret_cast<int *>(s.Ev + q);
         s.Path = s.MinCol + q;
         s.Zn = s.Path + 2 * q;
+        s.tvn = s.Zn + p.dc_max + 1;
+        s.tgf = s.tvn + p.dc_max;
+        s.tinv = s.tgf + p.dc_max;
+        s.mn = reinterpret_cast<float *>(s.tinv + p.dc_max);
     }
     int it = 0, ok = 0;
     while (it < p.maxit) {
@@ -699,8 +731,8 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
         }
         const int rounds = (M + groups - 1) / groups;
         for (int r = 0; r < rounds; r++) {
-            const int row = r * groups + g;
-            tmm_check(p, row, a, g < groups && row < M, s, LLR, c2v, layered);
+            const int row = r * groups + g, nrow = row + groups;
+            tmm_check(p, row, nrow < M ? nrow : -1, a, g < groups && row < M, s, LLR, c2v, layered);
         }
     }
     if (tid == 0) {
@@ -1048,7 +1080,7 @@ extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, ui
             w = (size_t)(T / q) * ((size_t)2 * c->dc_max * q);
         else
             w = (size_t)((o->algo == NB_ALGO_LAYERED_TMM) ? 1 : T / q) *
-                (((size_t)2 * c->dc_max * q + 9 * q + c->dc_max + 1 + 3) & ~(size_t)3);
+                tmm_group_floats(q, c->dc_max);
         return (w + 3) & ~(size_t)3;
     };
     const size_t slot_floats = nb_slot_floats(o->algo, N, M, q, c->dv_max, c->dc_max);
