@@ -30,9 +30,17 @@
 
 // Tuning switches; the defaults are the winners of A/B runs on B200 (tools/ab, J15_L30_Z1280, 10 it):
 //   LDPC_LOAD_DEPTH    8  channel-value vectors in flight per thread in the load phase
-//   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values (on: evicts messages, +4 %)
+//   LDPC_L2_PREFETCH   0  L2 prefetch of the CTA's next group of channel values: 1 = at the start of this group's
+//                         decode (evicts messages, +4 % time), 2 = before the LAST iteration, when the messages are
+//                         dead (+6 %: 60 prefetch instructions per thread and group cost more than the wait they save)
+//   LDPC_SKIP_LAST_ST  1  the last iteration of a fixed-iteration decode does not store its messages (nobody reads
+//                         them): J15_L30_Z1280 7.44 -> 7.37 ms; only for buckets <= 12 — in the register-bound
+//                         high-degree buckets the extra predicate costs more (PON 5.81 -> 6.23 ms)
 #ifndef LDPC_L2_PREFETCH
 #define LDPC_L2_PREFETCH 0
+#endif
+#ifndef LDPC_SKIP_LAST_ST
+#define LDPC_SKIP_LAST_ST 1
 #endif
 //   LDPC_HI_PRELOAD    0  degree buckets above 12 load a row's old messages at the start of the row instead of one
 //                         step ahead: 16-32 fewer live registers in phase 2 (B200, PON: 39.4 -> 41.6 Gbit/s)
@@ -178,7 +186,7 @@ struct MsgLayout {
 // (`ld_next`: the load is issued between the two phases, so its latency hides under phase 2).
 template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const LayeredParams &p, int off, int dc_rt,
-                                              int Z4, uint4 *msgp, const uint4 *nx, bool ld_next,
+                                              int Z4, uint4 *msgp, const uint4 *nx, bool ld_next, bool st_msgs,
                                               unsigned (&mw)[MsgLayout<DCHI>::WORDS], __half2 amaxp, __half2 bmul,
                                               __half2 nbias, unsigned c9b)
 {
@@ -270,7 +278,7 @@ __device__ __forceinline__ void process_row_x(unsigned isb, int i4, const Layere
         } else {
             mn[k & 7] = 0x7F7F7F7Fu;  // padding / absent edges: message 0
         }
-        if ((k & 7) == 7) msg_store8(msgp + 2 * (k >> 3), mn);
+        if ((k & 7) == 7 && st_msgs) msg_store8(msgp + 2 * (k >> 3), mn);
     }
 }
 
@@ -301,7 +309,7 @@ __device__ __noinline__ void generic_rows(unsigned sbase, const LayeredParams &p
         unsigned mw[MsgLayout<DCHI>::WORDS];  // out of line: this path loads its messages itself
         if (!FIRST) msg_load<MsgLayout<DCHI>::CH>(msgl + (size_t)i * RS, mw);
         process_row_x<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, msgl + (size_t)i * RS, nullptr,
-                                                false, mw, amaxp, bmul, nbias, c9b);
+                                                false, true, mw, amaxp, bmul, nbias, c9b);
     }
 }
 
@@ -320,12 +328,14 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
         // preloaded only if a sweep that reads messages follows
         const uint4 *nxl = msgs + (size_t)((r + 1 == p.J) ? 0 : r + 1) * Z * RS;
         const bool next_layer_reads = (!FIRST || r == p.J - 1) && !(last && r == p.J - 1);
+        // the messages of the last sweep are read by nobody (debug dumps excepted)
+        const bool st_msgs = !(LDPC_SKIP_LAST_ST && DCHI <= 12 && last) || p.dbg_msg != nullptr;
 #define LDPC_ROWS(DCX)                                                                                        \
     for (int i = tid; i < Z; i += T) {                                                                        \
         const uint4 *nx;                                                                                      \
         const bool ldn = next_block<DCHI, FIRST>(msgl, nxl, i, T, Z, next_layer_reads, nx);                   \
         process_row_x<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, msgl + (size_t)i * RS, nx, ldn, \
-                                              mw, amaxp, bmul, nbias, c9b);                                   \
+                                              st_msgs, mw, amaxp, bmul, nbias, c9b);                          \
     }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
@@ -608,8 +618,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         __syncthreads();
         LDPC_STRESS_POINT(5);
         // pull the channel values of this CTA's next group towards L2 while this group is decoded
-        if (LDPC_L2_PREFETCH && !dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
-            p.layout == LDPC_LAYOUT_NF) {
+        const bool can_prefetch = !dynamic && g + (int)gridDim.x < p.num_groups && p.llr_dtype == LDPC_DTYPE_FP32 &&
+                                  p.layout == LDPC_LAYOUT_NF;
+        if (LDPC_L2_PREFETCH == 1 && can_prefetch) {
             const float *y = reinterpret_cast<const float *>(p.llr) + 4 * (size_t)(g + gridDim.x);
             for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
         }
@@ -619,6 +630,13 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
         unsigned rw[MsgLayout<DCMAX>::WORDS];  // the old messages of the thread's next step
         while (it < p.iters) {
             it++;
+            if (LDPC_L2_PREFETCH == 2 && can_prefetch && it == p.iters) {
+                // the next group's 16 bytes per code bit: by the time this group's last sweep and output are done
+                // they wait in L2 (the load phase at the start of a group otherwise waits for HBM with nothing to
+                // overlap: one CTA per SM for the big codes)
+                const float *y = reinterpret_cast<const float *>(p.llr) + 4 * (size_t)(g + gridDim.x);
+                for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
+            }
             if (it == 1)
                 sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias, c9b);
             else
