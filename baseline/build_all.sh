@@ -14,3 +14,12 @@ $B C3_time         12 69  256 PON_LDPC.txt              4096  10   4096  1 fixed
 $B C1_time_literal  4 24   96 J4_L24_Z96_BlockH.txt     4096  10   4096  1 literal
 $B C1_fer_literal   4 24   96 J4_L24_Z96_BlockH.txt      256  10   1024  1 literal
 $B C1_fer_fixed     4 24   96 J4_L24_Z96_BlockH.txt      256  10   1024  1 fixed
+# non-binary: the reference's whole simulator, GPU decoders (frame at a time), 20 iterations.  BDS is the only matrix its
+# hard-coded codeword belongs to (main.cu:190-212 always sends CodeWord_sym_test): for C4 / C5 the word is not a
+# codeword, the decoder runs all maxIT iterations on every frame — the time per frame is what is taken from those runs.
+N="$here/build_ref_nb_gpu.sh"
+#   name      matrix                              constellation                     nqam gfq dc dv nm nc it method snr  errs frames
+$N BDS_ems   BDS.576.288.GF.64.txt               ./Constellation/BPSK.txt             2  64  4  2  2  2 20 0      2.5  50   400
+$N BDS_tmm   BDS.576.288.GF.64.txt               ./Constellation/BPSK.txt             2  64  4  2  2  2 20 1      2.5  50   400
+$N C4_ems    LDPC_N576_K288_GF64_d1_exp.txt      ./Constellation/GRAY_64QAM.txt      64  64  4  2  2  2 20 0      10.0 20   100
+$N C5_tmm    LDPC_N576_K480_GF256_exp.txt        ./Constellation/BPSK.txt             2 256 12  2  2  2 20 1      4.5  20   100
