@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/ldpc_b200.h"
@@ -25,6 +26,11 @@ struct nb_ldpc_code {
     float *d_cre, *d_cim;
     void *scratch;
     size_t scratch_bytes;
+    // calls on one handle serialise on its scratch arena: `call_mu` for host threads, `last_use` (recorded on the
+    // call's stream) is waited for by the next call's stream — same contract as the binary handle (common.h)
+    std::mutex call_mu;
+    cudaEvent_t last_use;
+    bool last_use_valid;
     // encoder cache (host), built lazily by nb_ldpc_encode_info: information positions, pivot column per reduced row,
     // and the dense map pivot symbol i = sum_j enc_P[i][j] * info symbol j
     int enc_state;

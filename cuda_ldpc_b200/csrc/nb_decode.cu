@@ -1036,8 +1036,36 @@ int nb_upload_tables(nb_ldpc_code *c)
 
 using namespace ldpcb;
 
+static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint16_t *hard_syms, int iters,
+                                  const nb_decode_opts_t *o);
+
 extern "C" int nb_ldpc_decode_batch(const nb_ldpc_code_t *cc, const void *in, uint16_t *hard_syms, int iters,
                                     const nb_decode_opts_t *o)
+{
+    if (!cc || !in || !hard_syms || !o || iters <= 0) return LDPC_ERR_ARG;
+    nb_ldpc_code *c = const_cast<nb_ldpc_code *>(cc);
+    // calls on one handle are safe from any host thread / stream and serialise on its scratch arena
+    std::lock_guard<std::mutex> lk(c->call_mu);
+    int prev = -1;
+    const bool bound = c->device >= 0;
+    if (bound) {  // run on the device the handle was bound to by its first decode, whatever the caller's current one is
+        LDPC_CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != c->device) LDPC_CUDA_TRY(cudaSetDevice(c->device));
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
+    int rc = LDPC_OK;
+    if (c->last_use_valid && cudaStreamWaitEvent(st, c->last_use, 0) != cudaSuccess) rc = LDPC_ERR_CUDA;
+    if (rc == LDPC_OK) rc = nb_decode_batch_locked(cc, in, hard_syms, iters, o);
+    if (c->device >= 0) {
+        if (!c->last_use && cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming) != cudaSuccess) c->last_use = nullptr;
+        if (c->last_use && cudaEventRecord(c->last_use, st) == cudaSuccess) c->last_use_valid = true;
+    }
+    if (bound && prev != c->device) (void)cudaSetDevice(prev);
+    return rc;
+}
+
+static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint16_t *hard_syms, int iters,
+                                  const nb_decode_opts_t *o)
 {
     if (!cc || !in || !hard_syms || !o || iters <= 0) return LDPC_ERR_ARG;
     if (o->struct_size != (int)sizeof(nb_decode_opts_t) || o->batch <= 0) return LDPC_ERR_ARG;

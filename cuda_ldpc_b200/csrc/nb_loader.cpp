@@ -109,6 +109,8 @@ extern "C" int nb_ldpc_load_code(const char *matrix, const char *gf_table, const
     c->d_mul = nullptr;
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    c->last_use = nullptr;
+    c->last_use_valid = false;
     int rc = LDPC_ERR_FORMAT;
     do {
         if (!(read_int(f, &c->N) && read_int(f, &c->M) && read_int(f, &c->q) && read_int(f, &c->dv_max) &&
@@ -246,6 +248,7 @@ extern "C" int nb_ldpc_load_code(const char *matrix, const char *gf_table, const
 extern "C" void nb_ldpc_free_code(nb_ldpc_code_t *c)
 {
     if (!c) return;
+    if (c->last_use) cudaEventDestroy(c->last_use);
     if (c->d_mul) {
         cudaFree(c->d_mul);
         cudaFree(c->d_inv);

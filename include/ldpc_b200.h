@@ -228,7 +228,8 @@ void nb_decode_opts_default(nb_decode_opts_t *opts);
 
 /* Replaces Demodulate + Decoding_EMS(_GPU) / Decoding_TMM(_GPU) / Decoding_layered_TMM
  * (NB/include/Decode_GPU.cuh:17,19; called from NB/src/Simulation.cpp:130-138), batched over F
- * frames.  hard_syms: uint16 [F][N].  iters = maxIT (NB/include/define.h:35).               */
+ * frames.  hard_syms: uint16 [F][N].  iters = maxIT (NB/include/define.h:35).  Threading as for the binary
+ * handle: calls on one handle are safe from any host thread / stream and serialise on its scratch arena.     */
 int nb_ldpc_decode_batch(const nb_ldpc_code_t *code, const void *in, uint16_t *hard_syms, int iters,
                          const nb_decode_opts_t *opts);
 
