@@ -522,8 +522,8 @@ __host__ __device__ constexpr size_t tmm_group_floats(int q, int dc_max)
 // shared memory once per row, and the LLR / c2v vectors of the row's edges are loaded four edges at a time
 // before the first of them is used (a loop of dependent load -> subtract -> store pairs serialised them): layered TMM
 // C5 126 -> 140, BDS 159 -> 170, C4 660 -> 688 info Mbit/s.  An L1 prefetch of the next row's vectors on top LOSES 4 %.
-__device__ void tmm_check(const NbParams &p, int row, int nrow, int a, bool act, const TmmShared &s, float *LLR,
-                          float *c2v, bool write_llr)
+__device__ void tmm_check(const NbParams &p, int row, int a, bool act, const TmmShared &s, float *LLR, float *c2v,
+                          bool write_llr)
 {
     const int q = p.q, w = act ? p.cw[row] : 0;
     if (act)
@@ -731,8 +731,8 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
         }
         const int rounds = (M + groups - 1) / groups;
         for (int r = 0; r < rounds; r++) {
-            const int row = r * groups + g, nrow = row + groups;
-            tmm_check(p, row, nrow < M ? nrow : -1, a, g < groups && row < M, s, LLR, c2v, layered);
+            const int row = r * groups + g;
+            tmm_check(p, row, a, g < groups && row < M, s, LLR, c2v, layered);
         }
     }
     if (tid == 0) {
