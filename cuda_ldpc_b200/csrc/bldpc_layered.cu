@@ -127,10 +127,26 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned s)
 }
 __device__ __forceinline__ unsigned sel(unsigned mask, unsigned a, unsigned b) { return (a & mask) | (b & ~mask); }
 
+// q = sat127(rint(y * scale)) without a float -> int conversion (F2I runs on the quarter-rate XU pipe): clamp in float
+// (the bounds are integers, so clamping commutes with the rounding; NaN -> -127 like the oracle's (int)rintf), then
+// add 1.5 * 2^23 — the sum's ulp is 1, so the FADD itself rounds to nearest-even and the low mantissa byte is q in two's
+// complement.
+__device__ __forceinline__ unsigned quant_bits(float y, float scale)
+{
+    const float v = fminf(fmaxf(__fmul_rn(y, scale), -127.0f), 127.0f);
+    return __float_as_uint(__fadd_rn(v, 12582912.0f));
+}
 __device__ __forceinline__ int quant(float y, float scale)
 {
-    int q = __float2int_rn(__fmul_rn(y, scale));
-    return max(-127, min(127, q));
+    return (int)(signed char)(quant_bits(y, scale) & 0xFFu);
+}
+// four values -> the biased APP word (byte j = q_j + 127): two's-complement bytes ^ 0x80 = q + 128, minus 1 per byte
+// (no borrow: every byte is >= 1)
+__device__ __forceinline__ unsigned quant4(float a, float b, float c, float d, float scale)
+{
+    const unsigned lo = prmt(quant_bits(a, scale), quant_bits(b, scale), 0x0040u);
+    const unsigned hi = prmt(quant_bits(c, scale), quant_bits(d, scale), 0x0040u);
+    return (prmt(lo, hi, 0x5410u) ^ 0x80808080u) - 0x01010101u;
 }
 
 // m' = m - floor(m * beta_num / 2^beta_shift), exact in fp16 for m <= 127, beta_num <= 8:
@@ -378,7 +394,8 @@ __device__ __forceinline__ unsigned syndrome_row(const unsigned char *app, const
 __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int g, unsigned fmask)
 {
     const int F = p.F, N = p.N, f0 = 4 * g;
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const bool per_bit_pass = p.out_format != LDPC_OUT_BITPACK || p.dbg_app != nullptr;
+    for (int n = threadIdx.x; per_bit_pass && n < N; n += blockDim.x) {
         const unsigned w = appw[n];
         // bit j of `bits` = hard decision of frame j (APP < 0 <=> byte + 1 < 128; bytes never exceed 254)
         const unsigned nb = ~(w + 0x01010101u);
@@ -406,14 +423,42 @@ __device__ void write_outputs(const unsigned *appw, const LayeredParams &p, int 
     if (p.out_format == LDPC_OUT_BITPACK) {
         unsigned *D = reinterpret_cast<unsigned *>(p.out);
         const int W = (N + 31) / 32;
-        const int lane = threadIdx.x & 31;
-        const int nround = (N + 31) & ~31;
-        for (int n = threadIdx.x; n < nround; n += blockDim.x) {  // blockDim is a multiple of 32
-            const unsigned w = (n < N) ? appw[n] + 0x01010101u : 0x80808080u;
+        if ((N & 31) == 0) {
+            // one thread per output word: 32 code bits x 4 frames.  (~w - 0x01..)'s bit 7 per byte lane = hard decision of
+            // that frame; shifted to bit k of its lane for code bit k of an octet, the byte lanes collect 8 decisions
+            // each; a 4 x 4 byte transpose (PRMT) turns the four octet words into one 32-bit word per frame.
+            // (The ballot version spent 7.5 instructions per decision, this one ~1: 4.9 % -> 0.7 % of the kernel's
+            // instructions for J15_L30_Z1280.)
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(appw);
+            for (int wi = threadIdx.x; wi < W; wi += blockDim.x) {
+                unsigned acc[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned b = __ballot_sync(0xffffffffu, ((w >> (8 * j + 7)) & 1u) == 0u);
-                if (lane == 0 && ((fmask >> j) & 1u)) D[(size_t)(f0 + j) * W + (n >> 5)] = b;
+                for (int o = 0; o < 4; o++) {
+                    const uint4 x = a4[8 * wi + 2 * o], y = a4[8 * wi + 2 * o + 1];
+                    const unsigned w8[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                    unsigned a = 0u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) a |= ((~(w8[k] + 0x01010101u) & 0x80808080u) >> 7) << k;
+                    acc[o] = a;
+                }
+                const unsigned t0 = prmt(acc[0], acc[1], 0x5140u), t1 = prmt(acc[2], acc[3], 0x5140u);
+                const unsigned t2 = prmt(acc[0], acc[1], 0x7362u), t3 = prmt(acc[2], acc[3], 0x7362u);
+                const unsigned o4[4] = {prmt(t0, t1, 0x5410u), prmt(t0, t1, 0x7632u), prmt(t2, t3, 0x5410u),
+                                        prmt(t2, t3, 0x7632u)};
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if ((fmask >> j) & 1u) D[(size_t)(f0 + j) * W + wi] = o4[j];
+            }
+        } else {
+            const int lane = threadIdx.x & 31;
+            const int nround = (N + 31) & ~31;
+            for (int n = threadIdx.x; n < nround; n += blockDim.x) {  // blockDim is a multiple of 32
+                const unsigned w = (n < N) ? appw[n] + 0x01010101u : 0x80808080u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const unsigned b = __ballot_sync(0xffffffffu, ((w >> (8 * j + 7)) & 1u) == 0u);
+                    if (lane == 0 && ((fmask >> j) & 1u)) D[(size_t)(f0 + j) * W + (n >> 5)] = b;
+                }
             }
         }
     }
@@ -530,9 +575,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 for (int u = 0; u < kLoadDepth; u++) {
                     const int n = n0 + u * T;
                     if (n < N)
-                        appw[n] = (unsigned)(quant(v[u].x, p.scale) + 127) | ((unsigned)(quant(v[u].y, p.scale) + 127) << 8) |
-                                  ((unsigned)(quant(v[u].z, p.scale) + 127) << 16) |
-                                  ((unsigned)(quant(v[u].w, p.scale) + 127) << 24);
+                        appw[n] = quant4(v[u].x, v[u].y, v[u].z, v[u].w, p.scale);
                 }
             }
         }
@@ -553,8 +596,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                     const int n = n0 + u * T;
                     if (n < N) {
                         const float2 a = __half22float2(u2h(v[u].x)), b = __half22float2(u2h(v[u].y));
-                        appw[n] = (unsigned)(quant(a.x, p.scale) + 127) | ((unsigned)(quant(a.y, p.scale) + 127) << 8) |
-                                  ((unsigned)(quant(b.x, p.scale) + 127) << 16) | ((unsigned)(quant(b.y, p.scale) + 127) << 24);
+                        appw[n] = quant4(a.x, a.y, b.x, b.y, p.scale);
                     }
                 }
             }

@@ -1,7 +1,7 @@
 // Host-side packing for the host-buffer path of ldpc_decode_batch (ldpc_decode_opts_t::host_pack_threads):
 // fp32 channel values [N][F] (the reference's Channel_Out layout, B/Simulation.cu:138) -> int8 [N][fc] of one
 // frame chunk, with the layered kernel's own quantisation rule q = sat127(rint(y * scale)) (round to nearest
-// even, like __float2int_rn; NaN -> 0), so the decode is bit-identical to copying the fp32 values — at a quarter
+// even; NaN -> -127 like the kernel's clamp and the oracle), so the decode is bit-identical to copying the fp32 values — at a quarter
 // of the PCIe bytes.  The loop is bound by the host's DRAM: it reads the fp32 values once and writes the bytes with
 // non-temporal stores (no read-for-ownership of the pinned staging buffer).  AVX-512 path chosen at run time
 // (__builtin_cpu_supports), portable scalar path otherwise; both follow the same rule bit for bit
@@ -19,7 +19,7 @@ inline signed char quant1(float y, float scale)
 {
     float v = nearbyintf(y * scale);
     v = v > 127.0f ? 127.0f : (v < -127.0f ? -127.0f : v);
-    return (v != v) ? (signed char)0 : (signed char)(int)v;
+    return (v != v) ? (signed char)-127 : (signed char)(int)v;
 }
 
 void quant_row_scalar(const float *__restrict__ y, signed char *__restrict__ q, int n, float scale)
@@ -28,13 +28,13 @@ void quant_row_scalar(const float *__restrict__ y, signed char *__restrict__ q, 
 }
 
 // 16 floats -> 16 bytes (low 128 bits): clamp in float (the bounds are integers, so clamping commutes with the
-// rounding), convert with the current rounding mode (nearest even), NaN lanes -> 0
+// rounding), convert with the current rounding mode (nearest even).  NaN lanes -> -127: max_ps returns its SECOND
+// operand when either is NaN, which is the kernel's fmaxf(NaN, -127) = -127
 __attribute__((target("avx512f,avx512bw"))) inline __m128i quant16(const float *y, __m512 vs)
 {
     const __m512 v = _mm512_mul_ps(_mm512_loadu_ps(y), vs);
-    const __mmask16 ord = _mm512_cmp_ps_mask(v, v, _CMP_ORD_Q);
     const __m512 c = _mm512_min_ps(_mm512_max_ps(v, _mm512_set1_ps(-127.0f)), _mm512_set1_ps(127.0f));
-    return _mm512_cvtsepi32_epi8(_mm512_maskz_cvtps_epi32(ord, c));
+    return _mm512_cvtsepi32_epi8(_mm512_cvtps_epi32(c));
 }
 
 // `ynext`: the row this thread converts next.  A row segment of a chunk is ~1.2 pages long and the next one lies

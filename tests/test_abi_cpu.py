@@ -93,7 +93,7 @@ def test_no_product_code_touches_the_oracle():
 
 def test_host_quantiser_follows_the_kernel_rule():
     """ldpcb_host_pack_nf (csrc/host_pack.cc, AVX-512 with non-temporal stores or scalar): q = sat127(rint(y * scale)),
-    ties to even, NaN -> 0 — the layered kernel's own load rule (bldpc_layered.cu `quant`), for ragged chunk widths,
+    ties to even, NaN -> -127 — the layered kernel's own load rule (bldpc_layered.cu `quant`), for ragged chunk widths,
     unaligned outputs and any thread count."""
     import ctypes as C
     import cuda_ldpc_b200 as m
@@ -110,7 +110,7 @@ def test_host_quantiser_follows_the_kernel_rule():
     for scale in (8.0, 1.0, 0.37):
         with np.errstate(invalid="ignore", over="ignore"):
             want = np.clip(np.rint(y * np.float32(scale)), -127, 127)
-        want = np.where(np.isnan(want), 0, want).astype(np.int8)
+        want = np.where(np.isnan(want), -127, want).astype(np.int8)
         for f0, fc, threads in ((0, F, 1), (3, 333, 2), (64, 640, 5), (1, 65, 3), (500, 7, 1)):
             buf = np.full(N * fc + 64, 77, np.int8)
             for shift in (0, 1, 13):  # output alignment relative to 64 bytes
