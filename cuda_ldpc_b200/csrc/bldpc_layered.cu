@@ -376,16 +376,16 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const LayeredParams
     }
 }
 
-// fail bits (0x80 per frame byte) of the checks this thread owns in layer r
-__device__ __forceinline__ unsigned syndrome_row(const unsigned char *app, const LayeredParams &p, int off, int dc,
-                                                 int i4, int Z4)
+// fail bits (0x80 per frame byte) of check row i (isb = shared-memory address of row 0's word + 4 i) of one layer
+__device__ __forceinline__ unsigned syndrome_row(unsigned isb, const LayeredParams &p, int off, int dc, int i4, int Z4)
 {
     unsigned x = (dc & 1) ? 0x80808080u : 0u;  // byte = APP + 127 (<= 254): negative <=> bit 7 of byte + 1 clear
+#pragma unroll 4
     for (int k = 0; k < dc; k++) {
-        const int e = off + k;
-        int col4 = i4 + 4 * (int)p.lt.shift[e];
-        col4 -= (col4 >= Z4) ? Z4 : 0;
-        x ^= *reinterpret_cast<const unsigned *>(app + (int)p.lt.col[e] * Z4 + col4) + 0x01010101u;
+        const int2 e = p.tab[off + k];  // the sweep's own table: {byte offset of row 0's bit, wrap threshold}
+        unsigned a = isb + (unsigned)e.x;
+        a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+        x ^= lds32(a) + 0x01010101u;
     }
     return x & 0x80808080u;
 }
@@ -692,9 +692,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 for (int j = 0; j < 4; j++) rbytes |= ((running >> j) & 1u) ? (0x80u << (8 * j)) : 0u;
                 unsigned fl = 0u;
                 for (int r = 0; r < p.J; r++) {
-                    const int dc = p.lt.dc[r], off = p.lt.off[r];
+                    const int dc = p.dc[r], off = p.off[r];
                     unsigned fail = 0u;
-                    for (int i = tid; i < Z; i += T) fail |= syndrome_row(smem, p, off, dc, 4 * i, Z4);
+                    for (int i = tid; i < Z; i += T) fail |= syndrome_row(sbase + 4u * i, p, off, dc, 4 * i, Z4);
                     fail = __reduce_or_sync(0xffffffffu, fail);
                     constexpr int kFlip = LDPC_R1_RACES ? 0 : 1;
                     if ((tid & 31) == 0 && fail) atomicOr(&s_fail[r & kFlip], fail);
