@@ -92,7 +92,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ CPU legs (oracle = checker / baseline only)
 
-def cpu_baseline_port(frames=4096):
+def cpu_baseline_port(frames=16384):
     """The C oracle (oracle/liboracle.so, OpenMP over frames) on a bounded sample of the workload."""
     import numpy as np
     lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
