@@ -51,6 +51,33 @@
 #define LDPC_LOAD_DEPTH 8
 #endif
 
+// Developer build (make lib VARIANT=_phase EXTRA=-DLDPC_PHASE_TIMERS=1; tools/ab/phases.py): thread 0 of every CTA
+// accumulates clock64() deltas per phase (0 load + quantise, 1 first sweep, 2 later sweeps, 3 syndrome pass, 4 outputs).
+#ifndef LDPC_PHASE_TIMERS
+#define LDPC_PHASE_TIMERS 0
+#endif
+#if LDPC_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[8];
+extern "C" void ldpcb_debug_phase_cycles(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 8);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+    }
+}
+#define LDPC_PHASE_MARK(k)                                                            \
+    do {                                                                              \
+        if (threadIdx.x == 0) {                                                       \
+            const long long now_ = clock64();                                         \
+            atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - phase_t0_));    \
+            phase_t0_ = now_;                                                         \
+        }                                                                             \
+    } while (0)
+#else
+#define LDPC_PHASE_MARK(k) ((void)0)
+#endif
+
 namespace ldpcb {
 
 struct LayeredParams {
@@ -530,6 +557,9 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             g = s_next;
         }
         if (g >= p.num_groups) break;
+#if LDPC_PHASE_TIMERS
+        long long phase_t0_ = clock64();
+#endif
         const int f0 = 4 * g;
         unsigned valid = 0;
 #pragma unroll
@@ -667,6 +697,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             for (int n = tid; n < N; n += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + (size_t)n * F));
         }
 
+        LDPC_PHASE_MARK(0);
         unsigned running = valid;  // frames not yet latched
         int it = 0;
         unsigned rw[MsgLayout<DCMAX>::WORDS];  // the old messages of the thread's next step
@@ -683,6 +714,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 sweep_layers<DCMAX, true>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias, c9b);
             else
                 sweep_layers<DCMAX, false>(sbase, p, rec, it == p.iters, rw, amaxp, bmul, nbias, c9b);
+            LDPC_PHASE_MARK(it == 1 ? 1 : 2);
             if (p.exit_mode == LDPC_EXIT_SYNDROME || it == p.iters) {
                 // The pass stops after the first layer that leaves every running frame with a failed check (the
                 // usual case until the last iterations: one layer of J is read instead of all) — the outcome
@@ -709,6 +741,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
                 const unsigned okmask = (((~fl) >> 7) & 1u) | (((~fl) >> 14) & 2u) | (((~fl) >> 21) & 4u) |
                                         (((~fl) >> 28) & 8u);
                 const unsigned finish = (it == p.iters) ? running : (running & okmask);
+                LDPC_PHASE_MARK(3);
                 if (finish) {
                     LDPC_STRESS_POINT(3);
                     write_outputs(appw, p, g, finish);
@@ -729,6 +762,7 @@ ldpc_layered_i8_kernel(const __grid_constant__ LayeredParams p)
             }
         }
         __syncthreads();  // everyone is done with appw before the next group's load
+        LDPC_PHASE_MARK(4);
         LDPC_STRESS_POINT(4);
     }
 }
