@@ -765,6 +765,58 @@ __device__ __forceinline__ void wht_stage_all(float *F, int q, int w, int a)
     }
 }
 
+// The same transform without a single barrier: one warp per vector, PER = q / 32 consecutive elements per lane — the
+// stages below PER stay inside the lane's registers, the others cross lanes by __shfl_xor.  Stage order and the operands
+// of every add / subtract are those of wht_stage_all (x = the element with the stage's bit clear: x + y, x - y), so
+// the results are bit-identical.  Measured in isolation (tools/ubench/wht_ab.cu, profiles/r02_wht_ab.txt): 6.7 G
+// transforms/s with the data on chip, HBM-bound at 3.1 G rows/s otherwise.
+template <int PER>
+__device__ __forceinline__ void wht_vectors_warp(float *F, int q, int w, int warp_in_group, int warps_per_group, int lane)
+{
+    for (int d = warp_in_group; d < w; d += warps_per_group) {
+        float v[PER];
+        float *row = F + d * q + lane * PER;
+#pragma unroll
+        for (int t = 0; t < PER; t++) v[t] = row[t];
+#pragma unroll
+        for (int len = 1; len < PER; len <<= 1)
+#pragma unroll
+            for (int t = 0; t < PER; t++)
+                if (!(t & len)) {
+                    const float x = v[t], y = v[t | len];
+                    v[t] = __fadd_rn(x, y);
+                    v[t | len] = __fsub_rn(x, y);
+                }
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1)
+#pragma unroll
+            for (int t = 0; t < PER; t++) {
+                const float o = __shfl_xor_sync(0xffffffffu, v[t], m);
+                v[t] = (lane & m) ? __fsub_rn(o, v[t]) : __fadd_rn(v[t], o);
+            }
+#pragma unroll
+        for (int t = 0; t < PER; t++) row[t] = v[t];
+    }
+}
+// all vectors of a row: warp form for q = 32 PER (ends with one barrier), staged form otherwise
+__device__ __forceinline__ void wht_all(float *F, int q, int w, int a)
+{
+    const int lane = a & 31, wg = a >> 5, nwg = q >> 5;
+    if (q == 256)
+        wht_vectors_warp<8>(F, q, w, wg, nwg, lane);
+    else if (q == 128)
+        wht_vectors_warp<4>(F, q, w, wg, nwg, lane);
+    else if (q == 64)
+        wht_vectors_warp<2>(F, q, w, wg, nwg, lane);
+    else if (q == 32)
+        wht_vectors_warp<1>(F, q, w, wg, nwg, lane);
+    else {
+        wht_stage_all(F, q, w, a);
+        return;
+    }
+    cta_sync();
+}
+
 // tree sum of q values spread over a warp (element a = lane + 32 t), result in every lane
 template <int PER>
 __device__ __forceinline__ float warp_tree_sum(float (&x)[PER], int q)
@@ -913,7 +965,7 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
                 F[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])] = v[a];
             }
             cta_sync();
-            wht_stage_all(F, q, w, a);
+            wht_all(F, q, w, a);
             for (int d = 0; d < w; d++) {  // products of the other edges' transforms, ascending edge position
                 float gy = 1.0f;
                 bool first = true;
@@ -925,18 +977,36 @@ __device__ void decode_fftbp(const NbParams &p, int f, float *lch, float *pch, f
                 G[d * q + a] = gy;
             }
             cta_sync();
-            wht_stage_all(G, q, w, a);
+            wht_all(G, q, w, a);
             for (int d = 0; d < w; d++) {  // permute back, clamp; F is dead and takes the clamped values
                 const float gv = G[d * q + gmul(p, a, p.c_gf[row * p.dc_max + d])];
                 F[d * q + a] = gv > 1e-30f ? gv : 1e-30f;
             }
             cta_sync();
-            for (int d = 0; d < w; d++) G[d * q + a] = F[d * q + a];
-            cta_sync();
-            for (int len = q / 2; len >= 1; len >>= 1) {  // tree sums of all output edges
-                if (a < len)
-                    for (int d = 0; d < w; d++) G[d * q + a] = __fadd_rn(G[d * q + a], G[d * q + a + len]);
+            if (q >= 32) {  // tree sums of all output edges: one warp per vector, no barrier inside (same pairing:
+                            // element a = lane + 32 t, strides q/2 ... 32 in the lane's registers, 16 ... 1 by shuffles)
+                const int lane_g = a & 31;
+                for (int d = a >> 5; d < w; d += q >> 5) {
+                    float sum;
+#define CALL(PER)                                                              \
+    {                                                                          \
+        float x[PER];                                                          \
+        _Pragma("unroll") for (int t = 0; t < PER; t++) x[t] = F[d * q + lane_g + 32 * t]; \
+        sum = warp_tree_sum<PER>(x, q);                                        \
+    }
+                    FFT_PER(CALL)
+#undef CALL
+                    if (lane_g == 0) G[d * q] = sum;  // G was consumed by the permutation above (behind the barrier)
+                }
                 cta_sync();
+            } else {
+                for (int d = 0; d < w; d++) G[d * q + a] = F[d * q + a];
+                cta_sync();
+                for (int len = q / 2; len >= 1; len >>= 1) {
+                    if (a < len)
+                        for (int d = 0; d < w; d++) G[d * q + a] = __fadd_rn(G[d * q + a], G[d * q + a + len]);
+                    cta_sync();
+                }
             }
             for (int d = 0; d < w; d++) c2v[((size_t)row * p.dc_max + d) * q + a] = __fdiv_rn(F[d * q + a], G[d * q]);
             cta_sync();
