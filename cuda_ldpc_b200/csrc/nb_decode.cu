@@ -701,25 +701,63 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
     while (it < p.maxit) {
         it++;
         if (!layered) {  // :423-434: LLR += sum_d c2v_d — cumulative over the iterations, as the reference
-            for (int i = tid; i < N * q; i += T) {
-                const int col = i / q, x = i - col * q;
-                float v = LLR[i];
-                for (int d = 0; d < p.vw[col]; d++)
-                    v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
-                LLR[i] = v;
+            if (T % q == 0) {  // thread = (column slot, symbol): no division per element, the column's edge list is uniform
+                const int x = tid % q;
+                for (int col = tid / q; col < N; col += T / q) {
+                    float v = LLR[col * q + x];
+                    for (int d = 0; d < p.vw[col]; d++)
+                        v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
+                    LLR[col * q + x] = v;
+                }
+            } else {
+                for (int i = tid; i < N * q; i += T) {
+                    const int col = i / q, x = i - col * q;
+                    float v = LLR[i];
+                    for (int d = 0; d < p.vw[col]; d++)
+                        v = __fadd_rn(v, c2v[((size_t)p.v_cn[col * p.dv_max + d] * p.dc_max + p.v_pos[col * p.dv_max + d]) * q + x]);
+                    LLR[i] = v;
+                }
             }
         }
         if (tid == 0) *s_fail = 0;
         cta_sync();
-        for (int col = tid; col < N; col += T) {  // d_DecideLLRVector :92-105 (first minimum)
-            float mn = INFINITY;
-            int best = 0;
-            for (int x = 0; x < q; x++)
-                if (LLR[col * q + x] < mn) {
-                    mn = LLR[col * q + x];
-                    best = x;
+        // d_DecideLLRVector :92-105 (first minimum).  Wide CTAs: one warp per column — lanes scan x = lane, lane + 32, ...
+        // ascending, then a warp argmin with the lowest x on ties (one thread per column walked q dependent loads
+        // serially: TMM C5 117 -> 125 info Mbit/s).  The 2-warp CTAs of the layered decoder keep one thread per column
+        // (the warp form costs them 5 %).
+        if (T >= 256) {
+            for (int col = tid >> 5; col < N; col += T >> 5) {
+                const int lane = tid & 31;
+                float mn = INFINITY;
+                int best = 0;
+                for (int x = lane; x < q; x += 32) {
+                    const float v = LLR[col * q + x];
+                    if (v < mn) {
+                        mn = v;
+                        best = x;
+                    }
                 }
-            sym[col] = (uint16_t)best;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float on = __shfl_xor_sync(0xffffffffu, mn, o);
+                    const int ox = __shfl_xor_sync(0xffffffffu, best, o);
+                    if (on < mn || (on == mn && ox < best)) {
+                        mn = on;
+                        best = ox;
+                    }
+                }
+                if (lane == 0) sym[col] = (uint16_t)best;
+            }
+        } else {
+            for (int col = tid; col < N; col += T) {
+                float mn = INFINITY;
+                int best = 0;
+                for (int x = 0; x < q; x++)
+                    if (LLR[col * q + x] < mn) {
+                        mn = LLR[col * q + x];
+                        best = x;
+                    }
+                sym[col] = (uint16_t)best;
+            }
         }
         cta_sync();
         syndrome(p, sym, s_fail);
