@@ -66,32 +66,56 @@ __device__ __forceinline__ int gmul(const NbParams &p, int a, int b)
 }
 
 // ---- Demodulate, NB/src/LDPC_Decoder.cpp:132-171 -------------------------------------------------
-__device__ void demodulate(const NbParams &p, int f, float *lch)
+// Thread = (symbol slot, field element) when the CTA width is a multiple of q (every launch shape of this file): no
+// division per element.  BPSK: the p per-bit terms -2 y_b / sigma^2 of a symbol are computed once into `tmp` (N * p
+// floats, the not yet initialised LLR area) instead of once per field element that contains the bit — the same terms
+// added in the same ascending-bit order, so L_ch is bit-identical (255 x 4 divisions per GF(256) symbol became 8).
+__device__ void demodulate(const NbParams &p, int f, float *lch, float *tmp)
 {
     const int q = p.q, N = p.N, tid = threadIdx.x, T = blockDim.x;
+    const bool grid2d = (T % q) == 0;
+    const int x0 = grid2d ? tid % q : 0, s0 = grid2d ? tid / q : 0, sstep = grid2d ? T / q : 1;
     if (p.in_kind == NB_IN_SYMBOL_LLR) {
         const float *src = reinterpret_cast<const float *>(p.in) + (size_t)f * N * (q - 1);
         for (int i = tid; i < N * (q - 1); i += T) lch[i] = src[i];
     } else if (p.in_kind == NB_IN_BPSK) {
         const float *rx = reinterpret_cast<const float *>(p.in) + (size_t)f * N * p.p;
         const float s2 = __fmul_rn(p.sigma, p.sigma);
-        for (int i = tid; i < N * (q - 1); i += T) {
-            const int s = i / (q - 1), a = i - s * (q - 1) + 1;
-            float v = 0.0f;
-            for (int b = 0; b < p.p; b++)
-                if (a & (1 << b)) v = __fadd_rn(v, __fdiv_rn(__fmul_rn(-2.0f, rx[s * p.p + b]), s2));
-            lch[i] = v;
+        for (int i = tid; i < N * p.p; i += T) tmp[i] = __fdiv_rn(__fmul_rn(-2.0f, rx[i]), s2);
+        cta_sync();
+        if (grid2d) {
+            if (x0 >= 1)
+                for (int s = s0; s < N; s += sstep) {
+                    float v = 0.0f;
+                    for (int b = 0; b < p.p; b++)
+                        if (x0 & (1 << b)) v = __fadd_rn(v, tmp[s * p.p + b]);
+                    lch[s * (q - 1) + x0 - 1] = v;
+                }
+        } else {
+            for (int i = tid; i < N * (q - 1); i += T) {
+                const int s = i / (q - 1), a = i - s * (q - 1) + 1;
+                float v = 0.0f;
+                for (int b = 0; b < p.p; b++)
+                    if (a & (1 << b)) v = __fadd_rn(v, tmp[s * p.p + b]);
+                lch[i] = v;
+            }
         }
+        cta_sync();  // tmp (= the LLR area) is free again
     } else {
         const float *rx = reinterpret_cast<const float *>(p.in) + (size_t)f * N * 2;
         const float den = __fmul_rn(__fmul_rn(2.0f, p.sigma), p.sigma);
         const float c0r = p.cre[0], c0i = p.cim[0];
-        for (int i = tid; i < N * (q - 1); i += T) {
-            const int s = i / (q - 1), a = i - s * (q - 1) + 1;
+        auto one = [&](int s, int a) {
             const float yr = rx[2 * s], yi = rx[2 * s + 1], car = p.cre[a], cai = p.cim[a];
             const float tr = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, yr), c0r), car), __fsub_rn(car, c0r));
             const float ti = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(2.0f, yi), c0i), cai), __fsub_rn(cai, c0i));
-            lch[i] = __fdiv_rn(__fadd_rn(tr, ti), den);
+            lch[s * (q - 1) + a - 1] = __fdiv_rn(__fadd_rn(tr, ti), den);
+        };
+        if (grid2d) {
+            if (x0 >= 1)
+                for (int s = s0; s < N; s += sstep) one(s, x0);
+        } else {
+            for (int i = tid; i < N * (q - 1); i += T) one(i / (q - 1), i % (q - 1) + 1);
         }
     }
 }
@@ -1090,7 +1114,7 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
     uint16_t *topsym = reinterpret_cast<uint16_t *>(topval + ntop);
     uint16_t *sym = topsym + ((ntop + 1) & ~(size_t)1);
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
-        demodulate(p, f, lch);
+        demodulate(p, f, lch, LLR);
         cta_sync();
         if (p.algo == NB_ALGO_EMS)
             decode_ems(p, f, lch, LLR, c2v, v2c, topval, topsym, sym, smem, &s_fail);
