@@ -748,8 +748,9 @@ __device__ void decode_tmm(const NbParams &p, int f, float *lch, float *LLR, flo
         // d_DecideLLRVector :92-105 (first minimum).  Wide CTAs: one warp per column — lanes scan x = lane, lane + 32, ...
         // ascending, then a warp argmin with the lowest x on ties (one thread per column walked q dependent loads
         // serially: TMM C5 117 -> 125 info Mbit/s).  The 2-warp CTAs of the layered decoder keep one thread per column
-        // (the warp form costs them 5 %).
-        if (T >= 256) {
+        // (the warp form costs them 5 %), and so do small fields (q = 16 with N = 9472 columns: a warp per column leaves
+        // half its lanes idle and serialises 1184 columns per warp — Tanner GF(16) TMM 1039 -> 732 info Mbit/s).
+        if (T >= 256 && q >= 64) {
             for (int col = tid >> 5; col < N; col += T >> 5) {
                 const int lane = tid & 31;
                 float mn = INFINITY;
