@@ -373,7 +373,9 @@ int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int
         int *a = (int *)malloc((size_t)N * sizeof(int));
         uint32_t *rec = (uint32_t *)calloc((size_t)M * 4, sizeof(uint32_t));
         for (int n = 0; n < N; n++)
-            a[n] = clampi((int)rintf(y[(size_t)n * F + f] * scale), -127, 127);
+            /* clamp in float first: (int) of +-inf / huge values / NaN is undefined in C (x86 returns INT_MIN for all of
+             * them, which would turn +inf into -127); NaN -> -127, like fmaxf(NaN, -127) in the kernel */
+            a[n] = (int)fminf(fmaxf(rintf(y[(size_t)n * F + f] * scale), -127.0f), 127.0f);
         int it = 0, okf = 0;
         while (it < maxit) {
             it++;
