@@ -28,6 +28,8 @@ __device__ __forceinline__ void nb_philox(uint32_t c[4], uint32_t k0, uint32_t k
     }
 }
 __device__ __forceinline__ float nb_u01(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+// radius uniform with 32-bit resolution near 0 (the normal's tail reaches 6.76 sigma; philox.cuh)
+__device__ __forceinline__ float nb_u01_tail(uint32_t x) { return __fmaf_rn((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
 // one thread = one channel use (a BPSK bit or a QAM symbol) of one frame
 __global__ void __launch_bounds__(256)
@@ -42,7 +44,7 @@ nb_modulate_awgn_kernel(float *__restrict__ out, int N, int p, int bpsk, int F, 
     const unsigned long long gf = first_frame + (unsigned long long)f;
     uint32_t c[4] = {(uint32_t)gf, (uint32_t)(gf >> 32), (uint32_t)i, 0x4E424C44u /* "NBLD" */};
     nb_philox(c, k0, k1);
-    const float r0 = sqrtf(-2.0f * __logf(nb_u01(c[0]))), r1 = sqrtf(-2.0f * __logf(nb_u01(c[2])));
+    const float r0 = sqrtf(-2.0f * __logf(nb_u01_tail(c[0]))), r1 = sqrtf(-2.0f * __logf(nb_u01_tail(c[2])));
     const float g0 = r0 * __cosf(6.283185307179586f * nb_u01(c[1]));  // the reference's cos branch
     const float g1 = r1 * __cosf(6.283185307179586f * nb_u01(c[3]));
     if (bpsk) {
