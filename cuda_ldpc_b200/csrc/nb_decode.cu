@@ -241,8 +241,11 @@ __device__ void ems_check_row_warp(const NbParams &p, int row, int d0, int d1, c
             const int nk = p.nm - 1, per_pair = nk * nk;
             const int leaves = (Nc == 2) ? (n * (n - 1) / 2) * per_pair : 0;
             for (int L = lane; L < leaves; L += 32) {
-                int P = L / per_pair;
-                const int kk = L - P * per_pair, k1 = 1 + kk / nk, k2 = 1 + kk - (kk / nk) * nk;
+                // Nm = 2 (the reference's EMS_NM): one leaf per pair, no index arithmetic — the two runtime divisions
+                // below were 8 % of the kernel's instructions for 3 leaves per output edge
+                int P = (nk == 1) ? L : L / per_pair;
+                const int kk = (nk == 1) ? 0 : L - P * per_pair;
+                const int k1 = (nk == 1) ? 1 : 1 + kk / nk, k2 = (nk == 1) ? 1 : 1 + kk - (kk / nk) * nk;
                 int j1 = 0;
                 for (int cnt = n - 1; P >= cnt; cnt--) {
                     P -= cnt;
