@@ -467,7 +467,7 @@ def run_ours(args):
                               "quantised to int8 by the library's host threads (the kernel's own rule, bit-identical) while "
                               "the previous chunk is copied and decoded" if packed else
                               "[N][F] fp32 pinned host buffer copied as fp32 (too few host cores per rank for the quantiser)",
-                    "host_pack_threads": "auto" if pack == 0 else pack, "host_cpus": cpus,
+                    "host_pack_threads": ("auto (12)" if packed else "auto (off: < 12 cpus)") if pack == 0 else pack, "host_cpus": cpus,
                     "host_bytes_read_per_step": Fe * code.N * 4,
                     "value_with_fp32_copy_over_pcie": e2e_copy_val,
                     "shape_device_in_host_out": {"value": e2e_b, "unit": "Gbit/s", "what": "Channel_Out on the device (the "

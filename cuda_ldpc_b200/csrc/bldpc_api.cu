@@ -105,10 +105,11 @@ static int pack_threads_of(const ldpc_decode_opts_t *o)
     if (o->llr_dtype != LDPC_DTYPE_FP32 || o->layout != LDPC_LAYOUT_NF) return 0;
     if (o->host_pack_threads > 0) return o->host_pack_threads;
     if (o->host_pack_threads < 0) return 0;
-    // auto: the quantiser beats the fp32 copy once it reads host DRAM faster than PCIe moves it (~55 GB/s), which
-    // takes about a dozen cores (profiles/r02_e2e.txt); fewer CPUs in this process' affinity mask -> plain copy
+    // auto: the quantiser is worth running once it reads host DRAM about as fast as PCIe moves it (~55 GB/s), which
+    // takes about a dozen cores; more threads than that only contend for the same DRAM (24-CPU box: 12 threads 10.4,
+    // 24 threads 9.9 Gbit/s, profiles/r02_e2e.txt); fewer CPUs in this process' affinity mask -> plain copy
     const int cpus = ldpcb_host_cpus();
-    return cpus >= 12 ? (cpus > 32 ? 32 : cpus) : 0;
+    return cpus >= 12 ? 12 : 0;
 }
 
 // pinned staging slots of the host-pack path, grown on demand

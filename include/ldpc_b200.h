@@ -118,8 +118,8 @@ typedef struct {
     /* Host path, layered int8, fp32 [N][F] input: the library can quantise each chunk to int8 on host threads (the
      * kernel's own rule q = sat127(rint(y*llr_scale)), bit-identical results) into pinned staging buffers and copy a
      * quarter of the bytes over PCIe; the quantisation of chunk k+1 runs under the copy and decode of chunk k.
-     * > 0: that many threads.  0 (default): automatic — the CPUs of the calling process' affinity mask (at most 32)
-     * when there are at least 12 of them, else a plain fp32 copy.  < 0: never (a busy host, or several ranks sharing
+     * > 0: that many threads.  0 (default): automatic — 12 threads when the calling process' affinity mask holds at
+     * least 12 CPUs, else a plain fp32 copy.  < 0: never (a busy host, or several ranks sharing
      * few cores).                                                                                            */
     int host_pack_threads;
 } ldpc_decode_opts_t;

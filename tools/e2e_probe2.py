@@ -18,7 +18,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         dt = (time.perf_counter() - t0) / 5
         print(f"  chunk_groups={os.environ.get('LDPC_B200_CHUNK_GROUPS','2')} pack={pack:3d}: {dt*1e3:7.2f} ms  {F*code.K/dt/1e9:6.2f} Gbit/s  host read {y.nbytes/dt/1e9:5.1f} GB/s", flush=True)
 else:
-    for cg, pct in (("2", "0"), ("2", "50"), ("2", "75"), ("2", "100"), ("2", "150"), ("4", "75"), ("4", "100"), ("1", "75"), ("1", "100")):
+    combos = (("2", "0"), ("2", "50"), ("2", "75"), ("2", "100"), ("2", "150"), ("4", "75"), ("4", "100"), ("1", "75"), ("1", "100"))
+    if len(sys.argv) > 1 and sys.argv[1] == "pct":
+        combos = tuple(("2", x) for x in sys.argv[2:])
+    print("host cpus", len(os.sched_getaffinity(0)), flush=True)
+    for cg, pct in combos:
         print("chunk groups", cg, "copy pct", pct, flush=True)
         subprocess.run([sys.executable, __file__, "child", "-1", "0", "12", "0", "12"],
                        env=dict(os.environ, LDPC_B200_CHUNK_GROUPS=cg, LDPC_B200_HYBRID_COPY_PCT=pct))
