@@ -90,8 +90,8 @@ class LdpcCode:
 
     def decode_channel(self, F, iters, sigma, *, seed=173, first_frame=0, codeword=None, early_exit=EXIT_SYNDROME,
                        out_format=OUT_BITPACK, llr_scale=8.0, msg_max=31, beta_num=0, beta_shift=0, stream=None, out=None,
-                       iters_out=None, ok_out=None, device=None):
-        """Layered int8 decode of F frames whose channel values are generated INSIDE the kernel
+                       iters_out=None, ok_out=None, device=None, msg_dtype=DTYPE_INT8):
+        """Layered int8 (or fp16: msg_dtype) decode of F frames whose channel values are generated INSIDE the kernel
         (y = 1 - 2c + sigma*n, the Philox stream of ldpc_awgn_bpsk keyed by the global frame index):
         the fused form of AWGNChannel_CPU + cudaMemcpy + LDPC_Decoder_GPU (Simulation.cu:137-143).
         codeword: CUDA uint8 tensor [N] or None (all-zero).  Device path only."""
@@ -106,7 +106,7 @@ class LdpcCode:
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         o = self.make_opts(F, layout=LAYOUT_NF, llr_dtype=DTYPE_CHANNEL, mem_space=MEM_DEVICE, schedule=SCHED_LAYERED,
-                           msg_dtype=DTYPE_INT8, early_exit=early_exit, out_format=out_format, llr_scale=llr_scale,
+                           msg_dtype=msg_dtype, early_exit=early_exit, out_format=out_format, llr_scale=llr_scale,
                            msg_max=msg_max, beta_num=beta_num, beta_shift=beta_shift, iters_out=iters_out.data_ptr(),
                            ok_out=ok_out.data_ptr(), stream=stream, channel_sigma=float(sigma), channel_seed=int(seed),
                            channel_first_frame=int(first_frame),
@@ -153,6 +153,9 @@ class LdpcCode:
                 if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
                     app = torch.zeros(N * F, dtype=torch.uint8, device=dev)
                     msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.int8, device=dev)
+                elif schedule == SCHED_LAYERED and msg_dtype == DTYPE_FP16:
+                    app = torch.zeros(N * F, dtype=torch.float16, device=dev)
+                    msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.float16, device=dev)
                 elif schedule == SCHED_LAYERED:
                     app = torch.zeros(N * F, dtype=torch.float32, device=dev)
                     msgs = torch.zeros(self.M * self.dc_max * F, dtype=torch.float32, device=dev)
@@ -195,6 +198,9 @@ class LdpcCode:
             if schedule == SCHED_LAYERED and msg_dtype == DTYPE_INT8:
                 app = np.zeros(N * F, np.int8)
                 msgs = np.zeros(self.M * self.dc_max * F, np.int8)
+            elif schedule == SCHED_LAYERED and msg_dtype == DTYPE_FP16:
+                app = np.zeros(N * F, np.float16)
+                msgs = np.zeros(self.M * self.dc_max * F, np.float16)
             elif schedule == SCHED_LAYERED:
                 app = np.zeros(N * F, np.float32)
                 msgs = np.zeros(self.M * self.dc_max * F, np.float32)

@@ -350,9 +350,10 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
     const bool layered_f32 = (o->schedule == LDPC_SCHED_LAYERED && o->msg_dtype == LDPC_DTYPE_FP32);
     const bool flooding = (o->schedule == LDPC_SCHED_FLOODING) || layered_f32;
     if (flooding && o->msg_dtype != LDPC_DTYPE_FP32) return LDPC_ERR_UNSUPPORTED;
-    if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8) return LDPC_ERR_UNSUPPORTED;
+    const bool layered_f16 = (!flooding && o->msg_dtype == LDPC_DTYPE_FP16);
+    if (!flooding && o->msg_dtype != LDPC_DTYPE_INT8 && !layered_f16) return LDPC_ERR_UNSUPPORTED;
     if (o->schedule == LDPC_SCHED_LAYERED && o->early_exit == LDPC_EXIT_GENIE) return LDPC_ERR_UNSUPPORTED;
-    if (fused_channel && (flooding || !(o->channel_sigma >= 0.0f))) return LDPC_ERR_UNSUPPORTED;  // layered int8 only
+    if (fused_channel && (flooding || !(o->channel_sigma >= 0.0f))) return LDPC_ERR_UNSUPPORTED;  // layered int8 / fp16 only
     int rc = ensure_device(c);
     if (rc != LDPC_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(o->stream);
@@ -368,9 +369,9 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
     const size_t in_bytes = fused_channel ? 0 : (size_t)c->N * F * dtype_bytes(o->llr_dtype);
     const size_t out_bytes = ldpc_out_bytes(c, F, o->out_format);
     const size_t dbg_app_bytes =
-        o->debug_app ? (size_t)c->N * F * (layered_f32 ? 4 : (flooding ? 0 : 1)) : 0;
+        o->debug_app ? (size_t)c->N * F * (layered_f32 ? 4 : (flooding ? 0 : (layered_f16 ? 2 : 1))) : 0;
     const size_t dbg_msg_bytes =
-        o->debug_msgs ? (size_t)c->M * c->dc_max * F * (flooding ? 4 : 1) : 0;  // fp32 messages / int8 c2v messages
+        o->debug_msgs ? (size_t)c->M * c->dc_max * F * (flooding ? 4 : (layered_f16 ? 2 : 1)) : 0;  // fp32 / fp16 / int8 c2v messages
 
     // ---- scratch carve-up (one arena per handle; decode calls on one handle serialise on it)
     size_t need = 0;
@@ -392,8 +393,9 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
     const size_t o_layer = need;  // the layered kernel sizes its own slice behind this offset
     unsigned char *base = nullptr;
     size_t layered_extra = 0;
-    if (!flooding && o->msg_dtype == LDPC_DTYPE_INT8) {
-        rc = layered_i8_scratch_bytes(c, F, o->beta_num, &layered_extra);
+    if (!flooding) {
+        rc = layered_f16 ? layered_f16_scratch_bytes(c, F, &layered_extra)
+                         : layered_i8_scratch_bytes(c, F, o->beta_num, &layered_extra);
         if (rc != LDPC_OK) return rc;
     }
     rc = ensure_scratch(c, need + layered_extra, reinterpret_cast<void **>(&base));
@@ -471,7 +473,7 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
         a.ch_seed = o->channel_seed;
         a.ch_first = o->channel_first_frame;
         a.ch_cw = o->channel_codeword;
-        rc = launch_layered_i8(c, a, st, &launches);
+        rc = layered_f16 ? launch_layered_f16(c, a, st, &launches) : launch_layered_i8(c, a, st, &launches);
         if (rc != LDPC_OK) return rc;
         if (host && o->debug_msgs)
             LDPC_CUDA_TRY(cudaMemcpyAsync(o->debug_msgs, d_dmsg, dbg_msg_bytes, cudaMemcpyDeviceToHost, st));

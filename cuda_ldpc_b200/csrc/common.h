@@ -109,6 +109,9 @@ struct LayeredArgs {
 // bytes of record scratch the layered kernels want for a batch of F frames
 int layered_i8_scratch_bytes(const ldpc_code *code, int F, int beta_num, size_t *bytes);
 int launch_layered_i8(const ldpc_code *code, const LayeredArgs &a, cudaStream_t st, int *launches);
+// fp16 message mode (bldpc_layered_f16.cu): same arguments; dbg_app / dbg_rec are binary16 [N][F] / [M][dc_max][F]
+int layered_f16_scratch_bytes(const ldpc_code *code, int F, size_t *bytes);
+int launch_layered_f16(const ldpc_code *code, const LayeredArgs &a, cudaStream_t st, int *launches);
 int launch_layered_f32_nf(const ldpc_code *code, const float *y_nf, int F, int iters, int exit_mode, float alpha,
                           float *app, float *msgs, unsigned char *hard_nf, int *iters_dev, int *ok_dev,
                           int *flag_scratch, cudaStream_t st, int *launches, bool may_block);

@@ -95,20 +95,25 @@ typedef struct {
     int llr_dtype;     /* LDPC_DTYPE_*   (input)                                                    */
     int mem_space;     /* LDPC_MEM_*     (llr, hard_bits, iters_out, ok_out all live there)         */
     int schedule;      /* LDPC_SCHED_*                                                              */
-    int msg_dtype;     /* LDPC_DTYPE_FP32 or LDPC_DTYPE_INT8: arithmetic of the messages            */
+    int msg_dtype;     /* arithmetic of the messages: LDPC_DTYPE_FP32 (flooding, layered), LDPC_DTYPE_INT8 or
+                          LDPC_DTYPE_FP16 (layered: the packed throughput modes, 4 / 2 codewords per word)  */
     int early_exit;    /* LDPC_EXIT_*                                                               */
     int out_format;    /* LDPC_OUT_*                                                                */
     float alpha;       /* fp32 layered: multiplies min1/min2 (1.0 = the reference's un-normalised rule) */
-    float llr_scale;   /* int8: q = sat127(rint(y*llr_scale)) when llr_dtype is fp32/fp16            */
-    int msg_max;       /* int8: message magnitude clip (1..127)                                     */
+    float llr_scale;   /* int8: q = sat127(rint(y*llr_scale)) when llr_dtype is fp32/fp16; fp16 messages: APP =
+                          f16(clamp(y*llr_scale, +-127)), no integer rounding                             */
+    int msg_max;       /* int8 / fp16: message magnitude clip (1..127)                              */
     int beta_num;      /* int8: m' = m - ((m*beta_num) >> beta_shift); 0 = the reference's un-normalised   */
-    int beta_shift;    /*       rule, (1,2) = x0.75, (1,3) = x0.875, (3,4) = x0.8125; beta_num <= 8          */
+    int beta_shift;    /*       rule, (1,2) = x0.75, (1,3) = x0.875, (3,4) = x0.8125; beta_num <= 8.
+                          fp16 messages: m' = m * (1 - beta_num / 2^beta_shift), one fp16 product         */
     int *iters_out;    /* [F] iterations executed per frame, or NULL                                */
     int *ok_out;       /* [F] 1 = syndrome satisfied (genie mode: all-zero info bits), or NULL      */
     void *stream;      /* cudaStream_t, NULL = default stream                                       */
-    void *debug_app;   /* optional device/host buffer receiving the final APP (layered) — tests     */
+    void *debug_app;   /* optional device/host buffer receiving the final APP [N][F] (layered: fp32 / int8 /
+                          binary16 by msg_dtype) — tests                                                  */
     void *debug_msgs;  /* optional buffer receiving the final check-to-variable messages [M][dc_max][F] (fp32 modes:
-                          float, the reference's Memory_RQ slots; layered int8: int8, 0 for absent edges) — tests */
+                          float, the reference's Memory_RQ slots; layered int8: int8, layered fp16: binary16; 0 for
+                          absent edges) — tests */
     /* fused channel (llr_dtype == LDPC_DTYPE_CHANNEL): y = 1 - 2c + sigma*N(0,1), Philox keyed by
      * (channel_seed, channel_first_frame + f, bit/4) exactly like ldpc_awgn_bpsk                    */
     float channel_sigma;

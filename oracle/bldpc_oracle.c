@@ -447,6 +447,146 @@ int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int
     return 0;
 }
 
+/* ------------------------------------------------------------------ layered fp16 */
+
+/* IEEE binary16 <-> binary32, round to nearest even, subnormals kept.  Every fp16 operation below is the float
+ * operation on the converted operands rounded back: for add/sub/mul of two 11-bit significands a 24-bit
+ * intermediate makes the double rounding innocuous (24 >= 2*11 + 2), so this IS the correctly rounded fp16 result
+ * — what HADD2 / HMUL2 compute on the GPU. */
+static inline float orc_h2f(uint16_t h)
+{
+    const uint32_t s = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 1023u;
+    uint32_t u;
+    if (e == 0) {
+        if (m == 0) u = s;
+        else {
+            float f = (float)m * (1.0f / 16777216.0f); /* m * 2^-24, exact */
+            memcpy(&u, &f, 4);
+            u |= s;
+        }
+    } else if (e == 31) u = s | 0x7F800000u | (m << 13);
+    else u = s | ((e + 112u) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static inline uint16_t orc_f2h(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint16_t s = (uint16_t)((u >> 16) & 0x8000u);
+    u &= 0x7FFFFFFFu;
+    if (u >= 0x7F800000u) return (uint16_t)(s | (u > 0x7F800000u ? 0x7E00u : 0x7C00u));
+    if (u >= 0x477FF000u) return (uint16_t)(s | 0x7C00u); /* >= 65520 rounds to inf */
+    if (u < 0x38800000u) {                                /* below 2^-14: subnormal result, unit 2^-24 */
+        float a;
+        memcpy(&a, &u, 4);
+        const float r = a * 16777216.0f; /* exact scaling */
+        return (uint16_t)(s | (uint16_t)lrintf(r)); /* nearest even in the default rounding mode; 1024 = smallest normal */
+    }
+    const uint32_t mant = u & 0x7FFFFFu, exp = (u >> 23) - 112u;
+    uint32_t h = (exp << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++; /* carries into the exponent correctly */
+    return (uint16_t)(s | h);
+}
+uint16_t orc_f16_from_f32(float f) { return orc_f2h(f); }
+float orc_f16_to_f32(uint16_t h) { return orc_h2f(h); }
+
+/*
+ * fp16 layered rules ("parity unpinned": ours, like the int8 rules; the CUDA kernel bldpc_layered_f16.cu must match
+ * bit for bit).  All values are binary16 patterns, all operations correctly rounded (nearest even):
+ *   APP[n]   = f16(clamp(y * scale, -127, 127))              (float product, float clamp, one rounding; NaN -> -127)
+ *   c2v      = +0 before the first iteration
+ *   t_k      = APP[v_k] - c2v_old_k ;  a_k = |t_k| (sign bit cleared) ;  neg_k = sign BIT of t_k (-0 counts)
+ *   min1 <= min2 = two smallest a_k (with multiplicity);  P = xor_k neg_k
+ *   m1'      = min(min1, amax) * c,  m2' = min(min2, amax) * c,   c = 1 - bnum / 2^bshift  (bnum = 0: no product)
+ *   new_k    = (P ^ neg_k ? -1 : +1) * (a_k == min1 ? m2' : m1')   (equal to the first-index rule: ties have min2 == min1)
+ *   APP[v_k] = min(max(t_k + new_k, -127), 127)
+ *   hard bit = sign BIT of APP.  ORC_EXIT_SYNDROME tests H x = 0 after each full iteration.
+ * app_out: [N][F] patterns; msg_out: [M][dc_max][F] patterns (absent edges 0).
+ */
+int orc_layered_f16(int J, int L, int Z, const int *H, const float *y, int F, int maxit, float scale, int amax,
+                    int bnum, int bshift, int exit_mode, int *D, int *iters, uint16_t *app_out, uint16_t *msg_out)
+{
+    const int N = L * Z, M = J * Z;
+    orc_layer *ly = build_layers(J, L, H);
+    if (amax < 1 || amax > 127) return -3;
+    int dcmax = 0;
+    for (int r = 0; r < J; r++) dcmax = ly[r].dc > dcmax ? ly[r].dc : dcmax;
+    const uint16_t amaxh = orc_f2h((float)amax);
+    const float c = 1.0f - (float)bnum / (float)(1 << bshift);
+#pragma omp parallel for schedule(dynamic)
+    for (int f = 0; f < F; f++) {
+        uint16_t *a = (uint16_t *)malloc((size_t)N * sizeof(uint16_t));
+        uint16_t *msg = (uint16_t *)calloc((size_t)M * dcmax, sizeof(uint16_t));
+        for (int n = 0; n < N; n++) a[n] = orc_f2h(fminf(fmaxf(y[(size_t)n * F + f] * scale, -127.0f), 127.0f));
+        int it = 0, okf = 0;
+        while (it < maxit) {
+            it++;
+            for (int r = 0; r < J; r++) {
+                const int dc = ly[r].dc;
+                for (int i = 0; i < Z; i++) {
+                    uint16_t *mr = msg + (size_t)(r * Z + i) * dcmax;
+                    uint16_t t[64];
+                    int v[64];
+                    unsigned min1 = 0x7C00u, min2 = 0x7C00u, P = 0;
+                    for (int k = 0; k < dc; k++) {
+                        v[k] = ly[r].col[k] * Z + (i + ly[r].shift[k]) % Z;
+                        t[k] = orc_f2h(orc_h2f(a[v[k]]) - orc_h2f(mr[k]));
+                        const unsigned ak = t[k] & 0x7FFFu; /* positive patterns order like integers */
+                        P ^= t[k] >> 15;
+                        if (ak < min1) {
+                            min2 = min1;
+                            min1 = ak;
+                        } else if (ak < min2)
+                            min2 = ak;
+                    }
+                    unsigned m1 = min1 < amaxh ? min1 : amaxh, m2 = min2 < amaxh ? min2 : amaxh;
+                    if (bnum != 0) {
+                        m1 = orc_f2h(orc_h2f((uint16_t)m1) * c);
+                        m2 = orc_f2h(orc_h2f((uint16_t)m2) * c);
+                    }
+                    for (int k = 0; k < dc; k++) {
+                        const unsigned ak = t[k] & 0x7FFFu;
+                        const unsigned s = P ^ (t[k] >> 15);
+                        const uint16_t nw = (uint16_t)((ak == min1 ? m2 : m1) | (s << 15));
+                        float x = orc_h2f(orc_f2h(orc_h2f(t[k]) + orc_h2f(nw)));
+                        uint16_t xh = orc_f2h(x);
+                        if (x > 127.0f) xh = orc_f2h(127.0f);
+                        if (x < -127.0f) xh = orc_f2h(-127.0f);
+                        a[v[k]] = xh;
+                        mr[k] = nw;
+                    }
+                }
+            }
+            if (exit_mode == ORC_EXIT_SYNDROME || it == maxit) {
+                okf = 1;
+                for (int r = 0; r < J && okf; r++)
+                    for (int i = 0; i < Z && okf; i++) {
+                        unsigned p = 0;
+                        for (int k = 0; k < ly[r].dc; k++) p ^= a[ly[r].col[k] * Z + (i + ly[r].shift[k]) % Z] >> 15;
+                        if (p) okf = 0;
+                    }
+                if (okf && exit_mode == ORC_EXIT_SYNDROME) break;
+            }
+        }
+        for (int n = 0; n < N; n++) {
+            D[(size_t)n * F + f] = a[n] >> 15;
+            if (app_out) app_out[(size_t)n * F + f] = a[n];
+        }
+        if (msg_out)
+            for (int m = 0; m < M; m++)
+                for (int k = 0; k < dcmax; k++) msg_out[((size_t)m * dcmax + k) * F + f] = msg[(size_t)m * dcmax + k];
+        D[(size_t)N * F + f] = okf;
+        iters[f] = it;
+        free(a);
+        free(msg);
+    }
+    free(ly);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ statistics + sim loop */
 
 int orc_statistic(orc_sim_counters *c, const int *codeword, const int *D, const int *iters,

@@ -71,6 +71,13 @@ int orc_layered_i8(int J, int L, int Z, const int *H, const float *y, int F, int
                    float scale, int amax, int bnum, int bshift, int exit_mode, int *D,
                    int *iters, int8_t *app_out, uint32_t *rec_out);
 
+/* Layered min-sum, fp16 state and messages (rules in bldpc_oracle.c "fp16 layered rules"; ours, parity unpinned).
+ * app_out (optional) binary16 patterns [N*F]; msg_out (optional) patterns [M*dc_max*F], absent edges 0.             */
+int orc_layered_f16(int J, int L, int Z, const int *H, const float *y, int F, int maxit, float scale, int amax,
+                    int bnum, int bshift, int exit_mode, int *D, int *iters, uint16_t *app_out, uint16_t *msg_out);
+uint16_t orc_f16_from_f32(float f);
+float orc_f16_to_f32(uint16_t h);
+
 /* true syndrome of hard bits x[N*F] (bit per int) -> ok[F] (1 = all checks satisfied) */
 void orc_syndrome_ok(int J, int L, int Z, const int *H, const int *D, int F, int *ok);
 

@@ -49,6 +49,11 @@ def oracle():
     lib.orc_layered_i8.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int,
                                                     C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    lib.orc_layered_f16.argtypes = lib.orc_layered_i8.argtypes
+    lib.orc_f16_from_f32.restype = C.c_uint16
+    lib.orc_f16_from_f32.argtypes = [C.c_float]
+    lib.orc_f16_to_f32.restype = C.c_float
+    lib.orc_f16_to_f32.argtypes = [C.c_uint16]
     lib.orc_flooding_fp32.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int)] * 4 + [
         C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
         C.c_void_p]
