@@ -110,23 +110,33 @@ __device__ __forceinline__ unsigned rec_message_rt(const unsigned *w, int k)
     return mag | sg;
 }
 
+// Edges whose shared-memory address is kept in a register between the two passes of a row (exact-degree paths);
+// above this degree the address is rebuilt from the table (4 instructions) to stay inside the register cap.
+#ifndef LDPC_F16_SAVE_ADDR_MAX
+#define LDPC_F16_SAVE_ADDR_MAX 32
+#endif
+
 // One check row of one layer for the 2 codewords of the group.  isb = shared-memory address of row 0's word + 4 i.
-template <int DCMAX, bool FIRST>
+// EXACT: the check degree is the template constant DC (no per-edge branches, every table entry is a constant-bank
+// load at an immediate offset).  !EXACT: DC is the bucket's maximum and edges k >= dc are predicated off.
+template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Params &p, int off, int dc, int Z4, uint4 *recp,
                                             __half2 amaxh, __half2 betac, bool store_rec)
 {
-    unsigned t[DCMAX], w[5];
-    if (!FIRST) rec_load<DCMAX>(recp, w);
-    unsigned m1 = 0x7C007C00u, m2 = 0x7C007C00u, par = 0u, A = 0u, B = 0u;
+    constexpr bool kSaveAddr = EXACT && DC <= LDPC_F16_SAVE_ADDR_MAX;
+    unsigned t[DC], addr[kSaveAddr ? DC : 1], w[5];
+    if (!FIRST) rec_load<DCHI>(recp, w);
+    unsigned m1 = 0x7C007C00u, m2 = 0x7C007C00u, par = 0u, A = 0u, B = 0u, held = 0u;
 #pragma unroll
-    for (int k = 0; k < DCMAX; k++) {
-        if (k < dc) {
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < dc) {
             const int2 e = p.tab[off + k];
             unsigned a = isb + (unsigned)e.x;
             a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+            if (kSaveAddr) addr[k] = a;
             const unsigned ap = lds32(a);
             unsigned tk = ap;
-            if (!FIRST) {
+            if (!FIRST) {  // the old message from the record: k == idx ? m2' : m1', sign bit k of both codewords
                 const unsigned eq = __heq2_mask(u2h(w[2]), u2h(kh(k)));
                 const unsigned mag = sel(eq, w[1], w[0]);
                 const unsigned sg = (w[k < 16 ? 3 : 4] << (k & 15)) & kSign2;
@@ -135,9 +145,18 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
             t[k] = tk;
             const unsigned ak = tk & kAbs2;
             par ^= tk;
-            // two smallest magnitudes with multiplicity; positive binary16 patterns order like unsigned integers
-            m2 = __vminu2(m2, __vmaxu2(m1, ak));
-            m1 = __vminu2(m1, ak);
+            // two smallest magnitudes with multiplicity; positive binary16 patterns order like unsigned integers.
+            // Exact paths take the edges in pairs: 5 min/max per 2 edges instead of 6
+            if (EXACT && (k & 1)) {
+                const unsigned lo = __vminu2(held, ak), hi = __vmaxu2(held, ak);
+                m2 = __vimin3_u16x2(m2, hi, __vmaxu2(m1, lo));
+                m1 = __vminu2(m1, lo);
+            } else if (EXACT && k + 1 < DC) {
+                held = ak;
+            } else {
+                m2 = __vminu2(m2, __vmaxu2(m1, ak));
+                m1 = __vminu2(m1, ak);
+            }
             if (k < 16)
                 A |= (tk & kSign2) >> (k & 15);
             else
@@ -155,11 +174,16 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
     const __half2 hi = __float2half2_rn(127.0f), lo = __float2half2_rn(-127.0f);
     unsigned idx = 0u;
 #pragma unroll
-    for (int k = 0; k < DCMAX; k++) {
-        if (k < dc) {
-            const int2 e = p.tab[off + k];
-            unsigned a = isb + (unsigned)e.x;
-            a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+    for (int k = 0; k < DC; k++) {
+        if (EXACT || k < dc) {
+            unsigned a;
+            if (kSaveAddr) {
+                a = addr[k];
+            } else {
+                const int2 e = p.tab[off + k];
+                a = isb + (unsigned)e.x;
+                a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+            }
             const unsigned tk = t[k];
             const unsigned eq = __heq2_mask(u2h(tk & kAbs2), u2h(m1));  // a_k == min1 (magnitudes: no NaN, no -0)
             idx = sel(eq, kh(k), idx);  // any index of a tied minimum serves: ties have m2' == m1'
@@ -170,20 +194,53 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
     }
     if (store_rec) {
         const unsigned flip = (pm >> 15) * 0xFFFFu;  // a lane's parity flips all of its sign bits
-        rec_store<DCMAX>(recp, h2u(m1s), h2u(m2s), idx, A ^ flip, B ^ flip);
+        rec_store<DCHI>(recp, h2u(m1s), h2u(m2s), idx, A ^ flip, B ^ flip);
     }
 }
 
-template <int DCMAX, bool FIRST>
+// Rows of a layer whose degree is outside the exact range of the kernel's bucket: predicated, out of line so that
+// its register needs do not leak into the allocation of the exact-degree paths.
+template <int DCHI, bool FIRST>
+__device__ __noinline__ void generic_rows(unsigned sbase, const F16Params &p, int off, int dc, uint4 *recl, __half2 amaxh,
+                                          __half2 betac, bool store_rec)
+{
+    const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
+    for (int i = threadIdx.x; i < Z; i += T)
+        process_row<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RecLayout<DCHI>::U4,
+                                              amaxh, betac, store_rec);
+}
+
+// One full iteration: all layers in order, the Z rows of a layer spread over the CTA.  Six exact degrees per bucket
+// (DCHI .. DCHI - 5), like the int8 mode.
+template <int DCHI, bool FIRST>
 __device__ __forceinline__ void sweep_layers(unsigned sbase, const F16Params &p, uint4 *rec, __half2 amaxh, __half2 betac,
                                              bool store_rec)
 {
-    const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
+    constexpr int U4 = RecLayout<DCHI>::U4;
+    const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x, tid = threadIdx.x;
     for (int r = 0; r < p.J; r++) {
         const int dc = p.dc[r], off = p.off[r];
-        for (int i = threadIdx.x; i < Z; i += T)
-            process_row<DCMAX, FIRST>(sbase + 4u * i, 4 * i, p, off, dc, Z4, rec + (size_t)(r * Z + i) * RecLayout<DCMAX>::U4,
-                                      amaxh, betac, store_rec);
+        uint4 *recl = rec + (size_t)r * Z * U4;
+#define LDPC_ROWS(DCX)                                                                                               \
+    for (int i = tid; i < Z; i += T)                                                                                 \
+        process_row<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * U4, amaxh, betac, \
+                                            store_rec);
+        if (dc == DCHI) {
+            LDPC_ROWS(DCHI)
+        } else if (DCHI >= 2 && dc == DCHI - 1) {
+            LDPC_ROWS((DCHI >= 2 ? DCHI - 1 : 1))
+        } else if (DCHI >= 3 && dc == DCHI - 2) {
+            LDPC_ROWS((DCHI >= 3 ? DCHI - 2 : 1))
+        } else if (DCHI >= 4 && dc == DCHI - 3) {
+            LDPC_ROWS((DCHI >= 4 ? DCHI - 3 : 1))
+        } else if (DCHI >= 5 && dc == DCHI - 4) {
+            LDPC_ROWS((DCHI >= 5 ? DCHI - 4 : 1))
+        } else if (DCHI >= 6 && dc == DCHI - 5) {
+            LDPC_ROWS((DCHI >= 6 ? DCHI - 5 : 1))
+        } else {
+            generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amaxh, betac, store_rec);
+        }
+#undef LDPC_ROWS
         __syncthreads();  // rows of one layer touch disjoint code bits; the next layer reads what this one wrote
         LDPC_STRESS_POINT(1);
     }
@@ -402,7 +459,7 @@ struct F16Kernel {
     }
 };
 
-#define LDPC_F16_BUCKETS(X) X(8) X(16) X(24) X(32)
+#define LDPC_F16_BUCKETS(X) X(4) X(8) X(12) X(16) X(20) X(24) X(28) X(32)
 
 struct F16Plan {
     int dcb, threads, grid, u4;
@@ -413,7 +470,7 @@ int plan_f16(const ldpc_code *c, int F, F16Plan *pl)
 {
     pl->smem = (size_t)c->N * 4;
     if (pl->smem > 227 * 1024) return LDPC_ERR_UNSUPPORTED;  // N > 58112: one group does not fit one SM
-    pl->dcb = (c->dc_max + 7) & ~7;
+    pl->dcb = (c->dc_max + 3) & ~3;
     int occ = 0, rc = LDPC_ERR_UNSUPPORTED;
     switch (pl->dcb) {
 #define X(D) case D: pl->u4 = RecLayout<D>::U4; break;
