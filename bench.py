@@ -252,6 +252,23 @@ def other_configs(m, torch, dev, peak, kw):
                         "kernel_ms": ms2, "avg_iterations": float(it_d.float().mean().item()),
                         "converged_fraction": float(ok_d.float().mean().item())})
         del y, out
+    for name in ("C2", "C1", "C3"):  # fp16 message mode (★g2): same workload, half2 state, 2 codewords per CTA
+        cfg = CONFIGS[name]
+        code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])
+        F = cfg["F"] // 2
+        sigma = m.sigma_from_snr(cfg["snr"][0], cfg["snr"][1], code.rate)
+        y = (1.0 + sigma * torch.randn(code.N, F, device=dev)).contiguous()
+        out = torch.empty(code.out_bytes(F, m.OUT_BITPACK), dtype=torch.uint8, device=dev)
+        it_d = torch.empty(F, dtype=torch.int32, device=dev)
+        ok_d = torch.empty(F, dtype=torch.int32, device=dev)
+        step = lambda: code.decode(y, ITERS, out=out, iters_out=it_d, ok_out=ok_d, **dict(kw, msg_dtype=m.DTYPE_FP16)).launches
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        _, ms, _ = timed_launches(step, 10, torch)
+        res.append({"config": name, "mode": "layered fp16 messages, 10 iterations fixed", "frames_per_launch": F,
+                    "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms})
+        del y, out
     for name, F in (("C1", 4096), ("C2", 1024)):  # flooding fp32: the reference's arithmetic, F = 4096 is its batch
         cfg = CONFIGS[name]
         code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])

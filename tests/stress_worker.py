@@ -24,6 +24,7 @@ orc.orc_awgn.argtypes = [C.POINTER(C.c_int), C.c_float, C.POINTER(C.c_int), C.PO
 orc.orc_layered_i8.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float,
                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                                 C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+orc.orc_layered_f16.argtypes = orc.orc_layered_i8.argtypes
 bad = 0
 
 
@@ -66,6 +67,38 @@ def binary(fname, geo, F, snr, iters, reps):
     print(f"{fname}: {reps} repeats x {F} frames, iterations {its.min()}..{its.max()}", flush=True)
 
 
+def binary_f16(fname, geo, F, snr, iters, reps):
+    """fp16 message mode (bldpc_layered_f16.cu): mixed early / late frames per 2-frame group, dynamic group scheduling."""
+    path = os.path.join(DATA, "bldpc", fname)
+    code, oc = m.LdpcCode(path, *geo), OracleCode(orc, path, *geo)
+    N = code.N
+    s = np.array([173, 173, 173], np.int32)
+    y = np.zeros(N * F, np.float32)
+    orc.orc_awgn(ip(s), orc.orc_sigma(1, snr, 1.0), None, fp(y), N, F)
+    y = y.reshape(N, F)
+    D = np.zeros((N + 1) * F, np.int32)
+    its = np.zeros(F, np.int32)
+    app = np.zeros(N * F, np.uint16)
+    msg = np.zeros(oc.M * code.dc_max * F, np.uint16)
+    assert orc.orc_layered_f16(oc.J, oc.L, oc.Z, ip(oc.H), fp(y), F, iters, 8.0, 31, 1, 3, 2, ip(D), ip(its),
+                               app.ctypes.data, msg.ctypes.data) == 0
+    D = D.reshape(N + 1, F)
+    assert its.min() < its.max()
+    yd = torch.as_tensor(y, device="cuda")
+    kw = dict(schedule=m.SCHED_LAYERED, msg_dtype=m.DTYPE_FP16, early_exit=m.EXIT_SYNDROME, msg_max=31, beta_num=1,
+              beta_shift=3)
+    for rep in range(reps):
+        r = code.decode(yd, iters, debug=True, **kw)
+        torch.cuda.synchronize()
+        check((r.D.cpu().numpy() == D).all(), f"{fname} fp16 device rep {rep}: hard bits / flags")
+        check((r.iters.cpu().numpy() == its).all(), f"{fname} fp16 device rep {rep}: iterations")
+        check((r.app.cpu().numpy().view(np.uint16) == app.reshape(N, F)).all(), f"{fname} fp16 device rep {rep}: APP")
+        check((r.msgs.cpu().numpy().view(np.uint16) == msg).all(), f"{fname} fp16 device rep {rep}: c2v messages")
+        rh = code.decode(y, iters, out_format=m.OUT_U8, **kw)
+        check((rh.D == D[:N]).all() and (rh.iters == its).all() and (rh.ok == D[N]).all(), f"{fname} fp16 host rep {rep}")
+    print(f"{fname} fp16: {reps} repeats x {F} frames, iterations {its.min()}..{its.max()}", flush=True)
+
+
 def nonbinary(matrix, q, const, snr, F, algos, iters, reps):
     import tempfile
     from cuda_ldpc_b200.gf import write_table_file
@@ -93,6 +126,8 @@ if what in ("all", "binary"):
     binary("J4_L24_Z96_BlockH.txt", (4, 24, 96), 1188, 2.7, 10, 6)
     binary("PON_LDPC.txt", (12, 69, 256), 600, 3.2, 10, 3)
     binary("J15_L30_Z1280_BlockH.txt", (15, 30, 1280), 600, -0.4, 10, 2)
+    binary_f16("J4_L24_Z96_BlockH.txt", (4, 24, 96), 1187, 2.7, 10, 4)
+    binary_f16("PON_LDPC.txt", (12, 69, 256), 599, 3.2, 10, 2)
 if what in ("all", "nb"):
     nonbinary("LDPC_N576_K288_GF64_d1_exp.txt", 64, "GRAY_64QAM.txt", 9.5, 600,
               (m.ALGO_EMS, m.ALGO_TMM, m.ALGO_LAYERED_TMM, m.ALGO_FFT_BP), 8, 3)
