@@ -115,18 +115,27 @@ __device__ __forceinline__ unsigned rec_message_rt(const unsigned *w, int k)
 #ifndef LDPC_F16_SAVE_ADDR_MAX
 #define LDPC_F16_SAVE_ADDR_MAX 32
 #endif
+// 1: a row's record is requested one row ahead (process_row); 0: at the row's first instruction
+#ifndef LDPC_F16_PRELOAD
+#define LDPC_F16_PRELOAD 0
+#endif
 
 // One check row of one layer for the 2 codewords of the group.  isb = shared-memory address of row 0's word + 4 i.
 // EXACT: the check degree is the template constant DC (no per-edge branches, every table entry is a constant-bank
 // load at an immediate offset).  !EXACT: DC is the bucket's maximum and edges k >= dc are predicated off.
+// w: this row's record, already in registers (!FIRST); nx / ld_next: the record of the thread's NEXT row is requested
+// at the start of this row and replaces w at its end, so the 20 warps of a 640-thread CTA never wait for a record
+// at a row's first instruction (records are thread-private: row i of every layer belongs to the same thread).
 template <int DC, int DCHI, bool FIRST, bool EXACT>
 __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Params &p, int off, int dc, int Z4, uint4 *recp,
-                                            __half2 amaxh, __half2 betac, bool store_rec)
+                                            __half2 amaxh, __half2 betac, bool store_rec, unsigned (&w)[5],
+                                            const uint4 *nx, bool ld_next)
 {
     constexpr bool kSaveAddr = EXACT && DC <= LDPC_F16_SAVE_ADDR_MAX;
-    unsigned t[DC], addr[kSaveAddr ? DC : 1], w[5];
-    if (!FIRST) rec_load<DCHI>(recp, w);
-    unsigned m1 = 0x7C007C00u, m2 = 0x7C007C00u, par = 0u, A = 0u, B = 0u, held = 0u;
+    unsigned t[DC], addr[kSaveAddr ? DC : 1], wn[5];
+    if (ld_next) rec_load<DCHI>(nx, wn);
+    __half2 m1 = u2h(0x7C007C00u), m2 = u2h(0x7C007C00u);  // +inf
+    unsigned par = 0u, A = 0u, B = 0u;
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
@@ -143,20 +152,13 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
                 tk = h2u(__hsub2(u2h(ap), u2h(mag | sg)));
             }
             t[k] = tk;
-            const unsigned ak = tk & kAbs2;
             par ^= tk;
-            // two smallest magnitudes with multiplicity; positive binary16 patterns order like unsigned integers.
-            // Exact paths take the edges in pairs: 5 min/max per 2 edges instead of 6
-            if (EXACT && (k & 1)) {
-                const unsigned lo = __vminu2(held, ak), hi = __vmaxu2(held, ak);
-                m2 = __vimin3_u16x2(m2, hi, __vmaxu2(m1, lo));
-                m1 = __vminu2(m1, lo);
-            } else if (EXACT && k + 1 < DC) {
-                held = ak;
-            } else {
-                m2 = __vminu2(m2, __vmaxu2(m1, ak));
-                m1 = __vminu2(m1, ak);
-            }
+            // two smallest magnitudes with multiplicity.  HMNMX2 takes |t| as an operand modifier, so the magnitude is
+            // never materialised (the integer min/max on the patterns would need it in a register: one more LOP3 per
+            // edge on the ALU pipe, which bounds this kernel — profiles/r02_ncu_layered_f16_C2.txt)
+            const __half2 ak = __habs2(u2h(tk));
+            m2 = __hmin2(m2, __hmax2(m1, ak));
+            m1 = __hmin2(m1, ak);
             if (k < 16)
                 A |= (tk & kSign2) >> (k & 15);
             else
@@ -164,14 +166,13 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
         }
     }
     // m' = min(m, amax) * c
-    __half2 m1s = __hmin2(u2h(m1), amaxh), m2s = __hmin2(u2h(m2), amaxh);
+    __half2 m1s = __hmin2(m1, amaxh), m2s = __hmin2(m2, amaxh);
     if (p.scale_on) {
         m1s = __hmul2(m1s, betac);
         m2s = __hmul2(m2s, betac);
     }
     const unsigned pm = par & kSign2;
     const unsigned m1x = h2u(m1s) ^ pm, m2x = h2u(m2s) ^ pm;
-    const __half2 hi = __float2half2_rn(127.0f), lo = __float2half2_rn(-127.0f);
     unsigned idx = 0u;
 #pragma unroll
     for (int k = 0; k < DC; k++) {
@@ -185,16 +186,20 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
                 a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
             }
             const unsigned tk = t[k];
-            const unsigned eq = __heq2_mask(u2h(tk & kAbs2), u2h(m1));  // a_k == min1 (magnitudes: no NaN, no -0)
+            const unsigned eq = __heq2_mask(__habs2(u2h(tk)), m1);  // |t_k| == min1 (magnitudes: no NaN, no -0)
             idx = sel(eq, kh(k), idx);  // any index of a tied minimum serves: ties have m2' == m1'
             const unsigned nw = sel(eq, m2x, m1x) ^ (tk & kSign2);
-            const __half2 x = __hmin2(__hmax2(__hadd2(u2h(tk), u2h(nw)), lo), hi);
-            sts32(a, h2u(x));
+            // no APP clamp: |APP| <= |channel| + dv * msg_max (+ rounding drift) <= 127 + 16 * 127, far inside binary16
+            sts32(a, h2u(__hadd2(u2h(tk), u2h(nw))));
         }
     }
     if (store_rec) {
         const unsigned flip = (pm >> 15) * 0xFFFFu;  // a lane's parity flips all of its sign bits
         rec_store<DCHI>(recp, h2u(m1s), h2u(m2s), idx, A ^ flip, B ^ flip);
+    }
+    if (ld_next) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) w[j] = wn[j];
     }
 }
 
@@ -205,9 +210,12 @@ __device__ __noinline__ void generic_rows(unsigned sbase, const F16Params &p, in
                                           __half2 betac, bool store_rec)
 {
     const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x;
-    for (int i = threadIdx.x; i < Z; i += T)
+    for (int i = threadIdx.x; i < Z; i += T) {
+        unsigned w[5];  // out of line: this path loads its records itself
+        if (!FIRST) rec_load<DCHI>(recl + (size_t)i * RecLayout<DCHI>::U4, w);
         process_row<DCHI, DCHI, FIRST, false>(sbase + 4u * i, 4 * i, p, off, dc, Z4, recl + (size_t)i * RecLayout<DCHI>::U4,
-                                              amaxh, betac, store_rec);
+                                              amaxh, betac, store_rec, w, nullptr, false);
+    }
 }
 
 // One full iteration: all layers in order, the Z rows of a layer spread over the CTA.  Six exact degrees per bucket
@@ -218,13 +226,23 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const F16Params &p,
 {
     constexpr int U4 = RecLayout<DCHI>::U4;
     const int Z = p.Z, Z4 = 4 * Z, T = blockDim.x, tid = threadIdx.x;
+    unsigned w[5];
+    if (LDPC_F16_PRELOAD && !FIRST && tid < Z)
+        rec_load<DCHI>(rec + (size_t)tid * U4, w);  // the one record per sweep that is waited for
     for (int r = 0; r < p.J; r++) {
         const int dc = p.dc[r], off = p.off[r];
         uint4 *recl = rec + (size_t)r * Z * U4;
+        const uint4 *nxl = rec + (size_t)(r + 1) * Z * U4;  // this thread's first row of the next layer
+        const bool more_layers = r + 1 < p.J;
 #define LDPC_ROWS(DCX)                                                                                               \
-    for (int i = tid; i < Z; i += T)                                                                                 \
+    for (int i = tid; i < Z; i += T) {                                                                               \
+        const bool same_layer = i + T < Z;                                                                           \
+        const uint4 *nx = same_layer ? recl + (size_t)(i + T) * U4 : nxl + (size_t)tid * U4;                         \
+        if (!LDPC_F16_PRELOAD && !FIRST) rec_load<DCHI>(recl + (size_t)i * U4, w);                                   \
         process_row<DCX, DCHI, FIRST, true>(sbase + 4u * i, 4 * i, p, off, DCX, Z4, recl + (size_t)i * U4, amaxh, betac, \
-                                            store_rec);
+                                            store_rec, w, nx,                                                        \
+                                            LDPC_F16_PRELOAD && !FIRST && (same_layer || more_layers));              \
+    }
         if (dc == DCHI) {
             LDPC_ROWS(DCHI)
         } else if (DCHI >= 2 && dc == DCHI - 1) {
@@ -239,6 +257,7 @@ __device__ __forceinline__ void sweep_layers(unsigned sbase, const F16Params &p,
             LDPC_ROWS((DCHI >= 6 ? DCHI - 5 : 1))
         } else {
             generic_rows<DCHI, FIRST>(sbase, p, off, dc, recl, amaxh, betac, store_rec);
+            if (LDPC_F16_PRELOAD && !FIRST && more_layers && tid < Z) rec_load<DCHI>(nxl + (size_t)tid * U4, w);
         }
 #undef LDPC_ROWS
         __syncthreads();  // rows of one layer touch disjoint code bits; the next layer reads what this one wrote

@@ -502,7 +502,8 @@ float orc_f16_to_f32(uint16_t h) { return orc_h2f(h); }
  *   min1 <= min2 = two smallest a_k (with multiplicity);  P = xor_k neg_k
  *   m1'      = min(min1, amax) * c,  m2' = min(min2, amax) * c,   c = 1 - bnum / 2^bshift  (bnum = 0: no product)
  *   new_k    = (P ^ neg_k ? -1 : +1) * (a_k == min1 ? m2' : m1')   (equal to the first-index rule: ties have min2 == min1)
- *   APP[v_k] = min(max(t_k + new_k, -127), 127)
+ *   APP[v_k] = t_k + new_k      (no clamp: |APP| <= |channel| + dv * amax + rounding drift, far inside binary16;
+ *                                t_k - c2v_old_k is never inf - inf because messages are <= amax)
  *   hard bit = sign BIT of APP.  ORC_EXIT_SYNDROME tests H x = 0 after each full iteration.
  * app_out: [N][F] patterns; msg_out: [M][dc_max][F] patterns (absent edges 0).
  */
@@ -551,11 +552,7 @@ int orc_layered_f16(int J, int L, int Z, const int *H, const float *y, int F, in
                         const unsigned ak = t[k] & 0x7FFFu;
                         const unsigned s = P ^ (t[k] >> 15);
                         const uint16_t nw = (uint16_t)((ak == min1 ? m2 : m1) | (s << 15));
-                        float x = orc_h2f(orc_f2h(orc_h2f(t[k]) + orc_h2f(nw)));
-                        uint16_t xh = orc_f2h(x);
-                        if (x > 127.0f) xh = orc_f2h(127.0f);
-                        if (x < -127.0f) xh = orc_f2h(-127.0f);
-                        a[v[k]] = xh;
+                        a[v[k]] = orc_f2h(orc_h2f(t[k]) + orc_h2f(nw));
                         mr[k] = nw;
                     }
                 }

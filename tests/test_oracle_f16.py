@@ -59,9 +59,7 @@ def np_layered_f16(oc, y, maxit, scale, amax, bnum, bshift):
             mag = np.where(ak == min1[:, None], m2[:, None], m1[:, None])
             s = np.logical_xor(P[:, None], neg)
             nw = np.where(s, -mag, mag).astype(np.float16)
-            x = (t + nw).astype(np.float16)
-            x = np.where(x > 127, np.float16(127), np.where(x < -127, np.float16(-127), x))
-            a[v] = x
+            a[v] = (t + nw).astype(np.float16)
             msg[rows[:, None], np.arange(len(cols))[None, :]] = nw
         ok = True
         for r in range(oc.J):
