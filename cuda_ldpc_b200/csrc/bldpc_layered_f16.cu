@@ -42,6 +42,7 @@ struct F16Params {
     float scale;
     float msg_max;
     float beta_c;       // 1 - beta_num / 2^beta_shift
+    unsigned one;       // 1 (LDPC_F16_MAD_ADDR)
     int scale_on;
     float ch_sigma;     // fused channel
     unsigned ch_k0, ch_k1;
@@ -67,8 +68,14 @@ __device__ __forceinline__ unsigned h2u(__half2 h) { return *reinterpret_cast<un
 __device__ __forceinline__ __half2 u2h(unsigned u) { return *reinterpret_cast<__half2 *>(&u); }
 __device__ __forceinline__ unsigned sel(unsigned mask, unsigned a, unsigned b) { return (a & mask) | (b & ~mask); }
 
+__device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 constexpr unsigned kSign2 = 0x80008000u;
-constexpr unsigned kAbs2 = 0x7FFF7FFFu;
 
 // binary16 pattern of the integer k (0..31) in both lanes: the edge index as the record stores it
 __host__ __device__ constexpr unsigned kh(int k)
@@ -115,6 +122,11 @@ __device__ __forceinline__ unsigned rec_message_rt(const unsigned *w, int k)
 #ifndef LDPC_F16_SAVE_ADDR_MAX
 #define LDPC_F16_SAVE_ADDR_MAX 32
 #endif
+// 1: the address additions of the first pass are written as multiply-adds (FMA pipe: 8 % busy) instead of IADD3 (ALU
+// pipe: 75 % busy, the bound) and both candidates (wrapped / not) are formed before the compare selects one
+#ifndef LDPC_F16_MAD_ADDR
+#define LDPC_F16_MAD_ADDR 1
+#endif
 // 1: a row's record is requested one row ahead (process_row); 0: at the row's first instruction
 #ifndef LDPC_F16_PRELOAD
 #define LDPC_F16_PRELOAD 0
@@ -134,20 +146,29 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
     constexpr bool kSaveAddr = EXACT && DC <= LDPC_F16_SAVE_ADDR_MAX;
     unsigned t[DC], addr[kSaveAddr ? DC : 1], wn[5];
     if (ld_next) rec_load<DCHI>(nx, wn);
-    __half2 m1 = u2h(0x7C007C00u), m2 = u2h(0x7C007C00u);  // +inf
+    __half2 m1 = u2h(0x7C007C00u), m2 = u2h(0x7C007C00u), held = u2h(0u);  // +inf
     unsigned par = 0u, A = 0u, B = 0u;
+    const unsigned dw = FIRST ? 0u : (w[0] ^ w[1]);
+    const unsigned one = p.one;  // a run-time 1: a literal would be folded back into an add
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         if (EXACT || k < dc) {
             const int2 e = p.tab[off + k];
-            unsigned a = isb + (unsigned)e.x;
-            a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+            unsigned a;
+            if (LDPC_F16_MAD_ADDR) {
+                const unsigned a0 = mad_u32((unsigned)e.x, one, isb), a1 = mad_u32((unsigned)e.x, one, isb - (unsigned)Z4);
+                a = (i4 >= e.y) ? a1 : a0;
+            } else {
+                a = isb + (unsigned)e.x;
+                a -= (i4 >= e.y) ? (unsigned)Z4 : 0u;
+            }
             if (kSaveAddr) addr[k] = a;
             const unsigned ap = lds32(a);
             unsigned tk = ap;
-            if (!FIRST) {  // the old message from the record: k == idx ? m2' : m1', sign bit k of both codewords
+            if (!FIRST) {  // the old message from the record: k == idx ? m2' : m1', sign bit k of both codewords.
+                // Two LOP3: m1' ^ (eq & (m1' ^ m2')), then | (signs << k & mask) — written as a select it took three
                 const unsigned eq = __heq2_mask(u2h(w[2]), u2h(kh(k)));
-                const unsigned mag = sel(eq, w[1], w[0]);
+                const unsigned mag = w[0] ^ (eq & dw);
                 const unsigned sg = (w[k < 16 ? 3 : 4] << (k & 15)) & kSign2;
                 tk = h2u(__hsub2(u2h(ap), u2h(mag | sg)));
             }
@@ -155,10 +176,19 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
             par ^= tk;
             // two smallest magnitudes with multiplicity.  HMNMX2 takes |t| as an operand modifier, so the magnitude is
             // never materialised (the integer min/max on the patterns would need it in a register: one more LOP3 per
-            // edge on the ALU pipe, which bounds this kernel — profiles/r02_ncu_layered_f16_C2.txt)
+            // edge on the ALU pipe, which bounds this kernel — profiles/r02_ncu_layered_f16_C2.txt).  Exact paths take
+            // the edges in pairs: 5 min/max per 2 edges instead of 6
             const __half2 ak = __habs2(u2h(tk));
-            m2 = __hmin2(m2, __hmax2(m1, ak));
-            m1 = __hmin2(m1, ak);
+            if (EXACT && (k & 1)) {
+                const __half2 lo = __hmin2(held, ak), hi = __hmax2(held, ak);
+                m2 = __hmin2(__hmin2(m2, hi), __hmax2(m1, lo));
+                m1 = __hmin2(m1, lo);
+            } else if (EXACT && k + 1 < DC) {
+                held = ak;
+            } else {
+                m2 = __hmin2(m2, __hmax2(m1, ak));
+                m1 = __hmin2(m1, ak);
+            }
             if (k < 16)
                 A |= (tk & kSign2) >> (k & 15);
             else
@@ -172,7 +202,7 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
         m2s = __hmul2(m2s, betac);
     }
     const unsigned pm = par & kSign2;
-    const unsigned m1x = h2u(m1s) ^ pm, m2x = h2u(m2s) ^ pm;
+    const unsigned m1x = h2u(m1s) ^ pm, dx = h2u(m1s) ^ h2u(m2s);  // m2x = m1x ^ dx
     unsigned idx = 0u;
 #pragma unroll
     for (int k = 0; k < DC; k++) {
@@ -188,7 +218,7 @@ __device__ __forceinline__ void process_row(unsigned isb, int i4, const F16Param
             const unsigned tk = t[k];
             const unsigned eq = __heq2_mask(__habs2(u2h(tk)), m1);  // |t_k| == min1 (magnitudes: no NaN, no -0)
             idx = sel(eq, kh(k), idx);  // any index of a tied minimum serves: ties have m2' == m1'
-            const unsigned nw = sel(eq, m2x, m1x) ^ (tk & kSign2);
+            const unsigned nw = (m1x ^ (eq & dx)) ^ (tk & kSign2);  // two LOP3
             // no APP clamp: |APP| <= |channel| + dv * msg_max (+ rounding drift) <= 127 + 16 * 127, far inside binary16
             sts32(a, h2u(__hadd2(u2h(tk), u2h(nw))));
         }
@@ -562,6 +592,7 @@ int launch_layered_f16(const ldpc_code *c, const LayeredArgs &a, cudaStream_t st
     p.msg_max = (float)a.msg_max;
     p.beta_c = 1.0f - (float)a.beta_num / (float)(1 << a.beta_shift);
     p.scale_on = a.beta_num != 0;
+    p.one = 1u;
     p.ch_sigma = a.ch_sigma;
     p.ch_k0 = (unsigned)a.ch_seed;
     p.ch_k1 = (unsigned)(a.ch_seed >> 32);
