@@ -4,8 +4,11 @@ value and every final check-to-variable message, compared as binary16 bit patter
 import numpy as np
 import pytest
 
-from conftest import ip, fp
-from test_binary_gpu import load, noisy
+import os
+import re
+
+from conftest import OracleCode, ip, fp
+from test_binary_gpu import ALL_FILES, BL, load, noisy
 
 import cuda_ldpc_b200 as m
 
@@ -137,3 +140,34 @@ def test_layered_f16_fused_channel_and_large_batch(oracle):
     i8 = code.decode(y, 10, schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=m.OUT_BITPACK, **kw)
     torch.cuda.synchronize()
     assert int(a.ok.sum()) >= int(i8.ok.sum()) - F // 50
+
+
+@pytest.mark.parametrize("fname", ALL_FILES)
+def test_layered_f16_every_shipped_code(oracle, fname):
+    """All 18 H files of the reference (dc 4..24, dv 2..15, Z 64..1280): every degree bucket, the exact-degree
+    instances and the out-of-line generic path of the fp16 kernel, bit-exact against the oracle (F odd: the last
+    group holds one codeword)."""
+    geo = (12, 69, 256) if fname == "PON_LDPC.txt" else tuple(int(x) for x in re.match(r"J(\d+)_L(\d+)_Z(\d+)", fname).groups())
+    path = os.path.join(BL, fname)
+    code, oc = m.LdpcCode(path, *geo), OracleCode(oracle, path, *geo)
+    F = 7 if code.N > 20000 else 11
+    snr = 10 * np.log10(1.0 / (2 * code.rate)) + 3.0 + (1.5 if code.rate > 0.7 else 0.0)
+    y = noisy(oracle, code.N, F, snr)
+    r = dec(code, y, 6, m.EXIT_SYNDROME, msg_max=31, beta_num=1, beta_shift=3)
+    D, its, app, msg = orc_f16(oracle, oc, y, 6, m.EXIT_SYNDROME, amax=31, bnum=1, bshift=3)
+    assert (r.D == D).all() and (r.iters == its).all(), fname
+    assert (r.app.view(np.uint16) == app).all() and (r.msgs.view(np.uint16) == msg).all(), fname
+
+
+@pytest.mark.parametrize("it", [1, 2])
+@pytest.mark.parametrize("mode", [m.EXIT_NONE, m.EXIT_SYNDROME])
+def test_layered_f16_one_and_two_iterations(oracle, it, mode):
+    """The first sweep has its own code path (no records to read) and the last fixed sweep skips the record stores."""
+    code, oc = load(oracle, "J10")
+    y = noisy(oracle, code.N, 9, 6.0)
+    for debug in (True, False):
+        r = dec(code, y, it, mode, debug=debug, msg_max=31, beta_num=1, beta_shift=3)
+        D, its, app, msg = orc_f16(oracle, oc, y, it, mode, amax=31, bnum=1, bshift=3)
+        assert (r.D == D).all() and (r.iters == its).all()
+        if debug:
+            assert (r.app.view(np.uint16) == app).all() and (r.msgs.view(np.uint16) == msg).all()
