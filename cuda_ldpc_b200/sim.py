@@ -60,7 +60,7 @@ class CudaBatchRunner:
     """channel + decode + statistic for one batch on the current CUDA device, all through the C-ABI"""
 
     def __init__(self, code, batch, *, maxit, schedule=B.SCHED_LAYERED, early_exit=B.EXIT_SYNDROME, msg_max=31,
-                 llr_scale=8.0, beta_num=0, beta_shift=0, codeword=None, seed=173):
+                 llr_scale=8.0, beta_num=0, beta_shift=0, codeword=None, seed=173, msg_dtype=None):
         import torch
         self.torch, self.code, self.batch, self.maxit, self.seed = torch, code, batch, maxit, seed
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -74,6 +74,8 @@ class CudaBatchRunner:
         self.cw = None if codeword is None else torch.as_tensor(np.asarray(codeword, np.uint8), device=dev)
         self.kw = dict(schedule=schedule, early_exit=early_exit, msg_max=msg_max, llr_scale=llr_scale,
                        beta_num=beta_num, beta_shift=beta_shift, out_format=B.OUT_BITPACK)
+        if msg_dtype is not None:  # layered: B.DTYPE_INT8 (default) or B.DTYPE_FP16
+            self.kw["msg_dtype"] = msg_dtype
 
     def reset(self):
         self.cnt.zero_()
