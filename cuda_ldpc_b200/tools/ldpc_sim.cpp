@@ -36,7 +36,7 @@ struct Args {
 static void usage()
 {
     printf("usage: ldpc_sim --code FILE [--J j --L l --Z z] [--snr a b step] [--snrtype 0|1] [--maxit n] [--batch F]\n"
-           "       [--layered] [--exit none|genie|syndrome] [--least-errors n] [--least-frames n] [--max-frames n]\n"
+           "       [--layered | --layered-fp16] [--exit none|genie|syndrome] [--least-errors n] [--least-frames n] [--max-frames n]\n"
            "       [--gpus g] [--seed s] [--msg-max m] [--beta num shift] [--llr-scale s] [--encode]\n");
 }
 
@@ -68,6 +68,7 @@ int main(int argc, char **argv)
         else if (s == "--maxit") a.maxit = atoi(next()), i++;
         else if (s == "--batch") a.batch = atoi(next()), i++;
         else if (s == "--layered") a.schedule = LDPC_SCHED_LAYERED, a.msg = LDPC_DTYPE_INT8;
+        else if (s == "--layered-fp16") a.schedule = LDPC_SCHED_LAYERED, a.msg = LDPC_DTYPE_FP16;  // fp16 message mode
         else if (s == "--exit") { std::string m = next(); i++; a.exit_mode = m == "none" ? LDPC_EXIT_NONE : m == "genie" ? LDPC_EXIT_GENIE : LDPC_EXIT_SYNDROME; }
         else if (s == "--least-errors") a.least_errors = atol(next()), i++;
         else if (s == "--least-frames") a.least_frames = atol(next()), i++;
@@ -120,7 +121,7 @@ int main(int argc, char **argv)
            info.N, info.J, info.L, info.Z);
     printf("* The encoding rate for current LDPC is %f\n* Maximum iterations for LDPC_decoder is %d\n", rate, a.maxit);
     printf("* schedule %s, messages %s, exit %s, %d frames per batch, %d GPU(s), codeword %s\n",
-           a.schedule == LDPC_SCHED_LAYERED ? "layered" : "flooding", a.msg == LDPC_DTYPE_INT8 ? "int8" : "fp32",
+           a.schedule == LDPC_SCHED_LAYERED ? "layered" : "flooding", a.msg == LDPC_DTYPE_INT8 ? "int8" : (a.msg == LDPC_DTYPE_FP16 ? "fp16" : "fp32"),
            a.exit_mode == LDPC_EXIT_NONE ? "none" : a.exit_mode == LDPC_EXIT_GENIE ? "genie" : "syndrome", a.batch,
            a.gpus, a.encode ? "random (encoded)" : "all-zero");
     printf("* The type of SNR is %s\n", a.snrtype == 0 ? "Eb/No" : "Es/No");
