@@ -15,7 +15,7 @@ for c in C2 C1 C3; do
   { echo "# ncu --set full --clock-control none: ldpc_layered_i8_kernel, $c, ${F[$c]} frames, 10 iterations fixed, msg_max 31, x0.875 (tools/ncu_layered.sh)";
     python tools/ncu_summary.py $rep.ncu-rep --json gpurun_out/${tag}_ncu_layered_i8.json $c ${F[$c]};
     (cd /tmp && ncu -i $rep.ncu-rep --page source --csv --print-source sass > $rep.csv 2>/dev/null);
-    echo "-- executed warp instructions by opcode: percent, per edge and 4 codewords (top 24)"; python tools/ncu_ophist.py $rep.csv ${EG[$c]} | head -25; } > $out 2>&1
+    echo "-- executed warp instructions by opcode: percent, per edge and 4 codewords (top 24)"; python tools/ncu_ophist.py $rep.csv ${EG[$c]} 2>/dev/null | head -25; } > $out 2>&1
   [ "$c" = C2 ] && cp $rep.ncu-rep gpurun_out/${tag}_c2.ncu-rep
   rm -f $rep.ncu-rep $rep.csv
 done

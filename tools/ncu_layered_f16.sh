@@ -15,6 +15,6 @@ for c in $cfgs; do
   { echo "# ncu --set full --clock-control none: ldpc_layered_f16_kernel, $c, ${F[$c]} frames, 10 iterations fixed, msg_max 31, x0.875 (tools/ncu_layered_f16.sh)";
     python tools/ncu_summary.py $rep.ncu-rep;
     (cd /tmp && ncu -i $rep.ncu-rep --page source --csv --print-source sass > $rep.csv 2>/dev/null);
-    echo "-- executed warp instructions by opcode: percent, per edge and 2 codewords (top 24)"; python tools/ncu_ophist.py $rep.csv ${EG[$c]} | head -25; } > $out 2>&1
+    echo "-- executed warp instructions by opcode: percent, per edge and 2 codewords (top 24)"; python tools/ncu_ophist.py $rep.csv ${EG[$c]} 2>/dev/null | head -25; } > $out 2>&1
   rm -f $rep.ncu-rep $rep.csv
 done
