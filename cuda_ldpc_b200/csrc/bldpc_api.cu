@@ -139,7 +139,9 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
     // Host cores reading DRAM and PCIe each sustain 50-60 GB/s on the B200 box; neither alone beats the other
     // (profiles/r02_e2e.txt), together they add up to 70-80 GB/s.  copy chunk = 1/2 of a pack chunk by default (swept 0-150 %): the
     // DMA engine also moves the pack chunks' int8 bytes (tuning: LDPC_B200_HYBRID_COPY_PCT, 0 = pack every chunk).
-    const int pack_threads = pack_threads_of(o);
+    const bool f16 = (o->msg_dtype == LDPC_DTYPE_FP16);  // fp16 message mode: fp32 copy chunks only (an int8 pack
+                                                          // would round what this mode exists not to round)
+    const int pack_threads = f16 ? 0 : pack_threads_of(o);
     const bool pack = pack_threads >= 1;
     int copy_pct = 50;
     if (const char *e = getenv("LDPC_B200_HYBRID_COPY_PCT")) copy_pct = atoi(e) < 0 ? 0 : (atoi(e) > 400 ? 400 : atoi(e));
@@ -152,7 +154,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
     const int W = (N + 31) / 32;
     const int Fmax = Fc > Fcopy ? Fc : Fcopy;
     size_t rec_bytes = 0;
-    int rc = layered_i8_scratch_bytes(c, Fmax, o->beta_num, &rec_bytes);
+    int rc = f16 ? layered_f16_scratch_bytes(c, Fmax, &rec_bytes) : layered_i8_scratch_bytes(c, Fmax, o->beta_num, &rec_bytes);
     if (rc != LDPC_OK) return rc;
     const size_t in_b = align_up((size_t)N * Fmax * esz), out_b = align_up(ldpc_out_bytes(c, Fmax, o->out_format));
     const size_t fl_b = align_up((size_t)Fmax * 4), slot = in_b + out_b + 2 * fl_b + align_up(rec_bytes);
@@ -221,7 +223,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
         a.ch_sigma = 0.0f;
         a.ch_seed = a.ch_first = 0;
         a.ch_cw = nullptr;
-        rc = launch_layered_i8(c, a, st, &launches);
+        rc = f16 ? launch_layered_f16(c, a, st, &launches) : launch_layered_i8(c, a, st, &launches);
         if (rc != LDPC_OK) break;
         unsigned char *h_out = reinterpret_cast<unsigned char *>(hard_bits);
         if (o->out_format == LDPC_OUT_BITPACK) {
@@ -361,7 +363,7 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
     // large host batches: chunked copy/compute overlap (2 groups per SM and chunk).  Measured on B200 for
     // the bench workload (1.45 GB of fp32 per call, pinned): 37.9 ms unchunked -> 28.5 ms with 8 chunks,
     // i.e. PCIe-bound (55 GB/s) instead of copy + decode in series (profiles/r01_h2d_probe.txt).
-    if (host && !flooding && !fused_channel && o->msg_dtype == LDPC_DTYPE_INT8 && !o->debug_app && !o->debug_msgs) {
+    if (host && !flooding && !fused_channel && !o->debug_app && !o->debug_msgs) {  // layered int8 / fp16
         int Fc = 4 * c->num_sms * 2;
         if (const char *e = getenv("LDPC_B200_CHUNK_GROUPS")) Fc = 4 * c->num_sms * (atoi(e) > 0 ? atoi(e) : 2);  // tuning
         if (F >= 2 * Fc) return decode_host_pipelined(c, llr, hard_bits, iters, o, Fc);

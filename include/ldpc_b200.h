@@ -120,7 +120,7 @@ typedef struct {
     uint64_t channel_seed;
     uint64_t channel_first_frame;
     const uint8_t *channel_codeword; /* device uint8 [N] broadcast to all frames, NULL = all-zero      */
-    /* Host path, layered int8, fp32 [N][F] input: the library can quantise each chunk to int8 on host threads (the
+    /* Host path, layered int8 (ignored by the fp16 message mode), fp32 [N][F] input: the library can quantise each chunk to int8 on host threads (the
      * kernel's own rule q = sat127(rint(y*llr_scale)), bit-identical results) into pinned staging buffers and copy a
      * quarter of the bytes over PCIe; the quantisation of chunk k+1 runs under the copy and decode of chunk k.
      * > 0: that many threads.  0 (default): automatic — 12 threads when the calling process' affinity mask holds at

@@ -171,3 +171,25 @@ def test_layered_f16_one_and_two_iterations(oracle, it, mode):
         assert (r.D == D).all() and (r.iters == its).all()
         if debug:
             assert (r.app.view(np.uint16) == app).all() and (r.msgs.view(np.uint16) == msg).all()
+
+
+@pytest.mark.parametrize("layout,fmt", [(m.LAYOUT_NF, m.OUT_BITPACK), (m.LAYOUT_NF, m.OUT_INT32_REF), (m.LAYOUT_FN, m.OUT_U8)])
+def test_layered_f16_chunked_host_path_equals_device_path(oracle, layout, fmt):
+    """Large host batches are decoded in chunks on two internal streams (copy / compute overlap, fp32 chunks only —
+    the host quantiser is an int8 feature): same bits, iteration counts and flags as one device-resident call."""
+    import torch
+    code, _ = load(oracle, "C1")
+    F = 3001  # not a multiple of the chunk (4 * SMs * 2) nor of 2
+    y = noisy(oracle, code.N, 64, 2.8)
+    y = np.tile(y, (1, 47))[:, :F] * (1.0 + 0.01 * np.arange(F, dtype=np.float32)[None, :] / F)
+    yy = np.ascontiguousarray(y if layout == m.LAYOUT_NF else y.T)
+    kw = dict(out_format=fmt, layout=layout, msg_max=31, beta_num=1, beta_shift=3, debug=False)
+    rh = dec(code, yy, 10, m.EXIT_SYNDROME, **kw)
+    rd = dec(code, torch.as_tensor(yy, device="cuda"), 10, m.EXIT_SYNDROME, **kw)
+    torch.cuda.synchronize()
+    got = rd.D.cpu().numpy()
+    assert (rh.D == (got.view(np.uint32) if fmt == m.OUT_BITPACK else got)).all()
+    assert (rh.iters == rd.iters.cpu().numpy()).all() and (rh.ok == rd.ok.cpu().numpy()).all()
+    assert rh.launches >= 3 and rd.launches == 1
+    rp = dec(code, yy, 10, m.EXIT_SYNDROME, host_pack_threads=3, **kw)  # ignored in this mode, not an error
+    assert (rp.D == rh.D).all() and (rp.iters == rh.iters).all()
