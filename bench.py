@@ -191,6 +191,14 @@ def b_cw_int8(cfg, iters):
     return iters * (2 * cfg["E"] + 2 * m_ * rec) + n * 4 + n // 8
 
 
+def b_cw_fp16(cfg, iters):
+    """SURVEY 8d's fp16 rows: w = 2, rec = 2*w + 1 + ceil(dc_max/8)"""
+    j, l, z = cfg["geo"]
+    n, m_ = l * z, j * z
+    rec = 4 + 1 + (cfg["dc_max"] + 7) // 8
+    return iters * (2 * cfg["E"] * 2 + 2 * m_ * rec) + n * 4 + n // 8
+
+
 def b_cw_flooding_fp32(cfg, iters):
     """the reference's own layout: (4E + 2N) * 4 bytes per codeword-iteration"""
     j, l, z = cfg["geo"]
@@ -266,8 +274,11 @@ def other_configs(m, torch, dev, peak, kw):
             step()
         torch.cuda.synchronize()
         _, ms, _ = timed_launches(step, 10, torch)
+        ach = F * b_cw_fp16(cfg, ITERS) / (ms * 1e-3) / 1e9
         res.append({"config": name, "mode": "layered fp16 messages, 10 iterations fixed", "frames_per_launch": F,
-                    "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms})
+                    "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms,
+                    "roofline_frac": ach / peak, "b_cw_bytes": b_cw_fp16(cfg, ITERS),
+                    "note": "above 1: SURVEY 8d's fp16 model streams the APP values through HBM; they live in shared memory here"})
         del y, out
     for name, F in (("C1", 4096), ("C2", 1024)):  # flooding fp32: the reference's arithmetic, F = 4096 is its batch
         cfg = CONFIGS[name]
