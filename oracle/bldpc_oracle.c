@@ -7,7 +7,8 @@
  *   VN/CN update rules, the genie batch-wide stop, Statistic and the per-SNR loop.
  * Defined here, not in the reference ("parity unpinned"):
  *   the circulant table (the reference's intended graph), the layered
- *   schedule, alpha, and the int8 fixed-point rules below.
+ *   schedule, alpha, the int8 fixed-point rules below and the fp16 rules further down
+ *   (orc_layered_f16; cross-checked against a numpy.float16 restatement, tests/test_oracle_f16.py).
  *
  * int8 layered rules (the CUDA kernel must match bit for bit):
  *   q        = clamp(rintf(y * scale), -127, 127)            APP[n] = q[n]
