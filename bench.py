@@ -432,6 +432,20 @@ def run_ours(args):
         return time.perf_counter() - t0, r.launches
 
     packed = pack > 0 or (pack == 0 and cpus >= 12)  # the library's own rule (csrc/bldpc_api.cu pack_threads_of)
+
+    def hybrid_h2d_bytes():
+        """bytes the hybrid feed copies per step: the chunk schedule of decode_host_pipelined (pack chunk = 2 groups per
+        SM as int8, copy chunk = half of that as fp32, alternating; csrc/bldpc_api.cu)"""
+        fc = 4 * torch.cuda.get_device_properties(dev).multi_processor_count * 2
+        fcopy = (fc * 50 // 100) & ~3
+        f0, k, nbytes = 0, 0, 0
+        while f0 < Fe:
+            is_pack = (k & 1) == 0 or fcopy == 0
+            n = min(Fe - f0, fc if is_pack else fcopy)
+            nbytes += n * code.N * (1 if is_pack else 4)
+            f0 += n
+            k += 1
+        return nbytes
     e2e_s, launches_e2e = time_host(e2e_steps, host_pack_threads=pack)
     parity_ok = host_parity()
     e2e_val = world * Fe * e2e_steps * K / allmax(e2e_s) / 1e9
@@ -457,6 +471,24 @@ def run_ours(args):
         step_dev_in_host_out()
     torch.cuda.synchronize()
     e2e_b = world * Fe * e2e_steps * K / allmax(time.perf_counter() - t0) / 1e9
+    parity_ok = parity_ok and host_parity()
+    # (d) a caller that already holds 8-bit channel values (llr_dtype = LDPC_DTYPE_INT8, the kernel's own quantiser rule
+    # applied upstream): a quarter of the PCIe bytes, no host pass over the data inside the call
+    yq = torch.clamp(torch.round(y * args.llr_scale), -127, 127).to(torch.int8)
+    yq_h = torch.empty(yq.shape, dtype=torch.int8).pin_memory()
+    yq_h.copy_(yq)
+    torch.cuda.synchronize()
+    del yq
+    yq_n = yq_h.numpy()
+    ho[:] = 0
+    for _ in range(2):
+        code.decode(yq_n, ITERS, **hkw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        code.decode(yq_n, ITERS, **hkw)
+    torch.cuda.synchronize()
+    e2e_d = world * Fe * e2e_steps * K / allmax(time.perf_counter() - t0) / 1e9
     parity_ok = parity_ok and host_parity()
     # (c) the simulation-loop shape (B/Simulation.cu:111-156): no input at all — the channel is generated inside the
     # kernel (LDPC_DTYPE_CHANNEL), Statistic runs on the device, 48 bytes of counters come back per batch
@@ -485,7 +517,7 @@ def run_ours(args):
                        "input": "fp32 [N][F] channel values resident in HBM (1.45 GB per step at F=9472, larger than L2)",
                        "output": "bit-packed hard decisions + per-frame syndrome flag",
                        "converged_fraction": ok_frac},
-            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": Fe * code.N if packed else h2d,
+            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": hybrid_h2d_bytes() if packed else h2d,
                     "d2h_bytes_per_step": d2h, "frames_per_step": Fe, "steps": e2e_steps,
                     "launches_per_step": launches_e2e, "cpu_affinity": numa, "parity_ok": parity_ok,
                     "parity_check": "hard bits, iteration counts and flags of every host-buffer shape below == the "
@@ -502,6 +534,10 @@ def run_ours(args):
                                                  "reference's own interface, B/LDPC_Decoder.cuh:5), hard decisions + "
                                                  "iterations + flags read back to pinned host memory every step",
                                                  "d2h_bytes_per_step": d2h},
+                    "shape_host_int8_in": {"value": e2e_d, "unit": "Gbit/s", "what": "pinned host int8 [N][F] input (caller "
+                                           "quantised with the kernel's rule; results equal the fp32 path's byte for "
+                                           "byte), same outputs to the host", "h2d_bytes_per_step": Fe * code.N,
+                                           "d2h_bytes_per_step": d2h},
                     "shape_sim_loop": {"value": e2e_c, "unit": "Gbit/s", "what": "fused device channel (LDPC_DTYPE_CHANNEL) -> "
                                        "decode -> ldpc_statistic -> 48 bytes of counters to the host per batch "
                                        "(B/Simulation.cu:111-156 without its F*N buffers)", "d2h_bytes_per_step": 48,
