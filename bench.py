@@ -433,20 +433,8 @@ def run_ours(args):
 
     packed = pack > 0 or (pack == 0 and cpus >= 12)  # the library's own rule (csrc/bldpc_api.cu pack_threads_of)
 
-    def hybrid_h2d_bytes():
-        """bytes the hybrid feed copies per step: the chunk schedule of decode_host_pipelined (pack chunk = 2 groups per
-        SM as int8, copy chunk = half of that as fp32, alternating; csrc/bldpc_api.cu)"""
-        fc = 4 * torch.cuda.get_device_properties(dev).multi_processor_count * 2
-        fcopy = (fc * 50 // 100) & ~3
-        f0, k, nbytes = 0, 0, 0
-        while f0 < Fe:
-            is_pack = (k & 1) == 0 or fcopy == 0
-            n = min(Fe - f0, fc if is_pack else fcopy)
-            nbytes += n * code.N * (1 if is_pack else 4)
-            f0 += n
-            k += 1
-        return nbytes
     e2e_s, launches_e2e = time_host(e2e_steps, host_pack_threads=pack)
+    h2d_e2e = int(m.lib.ldpc_last_h2d_bytes(code.handle))  # what the library uploaded in the last step (int8 + fp32 chunks)
     parity_ok = host_parity()
     e2e_val = world * Fe * e2e_steps * K / allmax(e2e_s) / 1e9
     h2d = Fe * code.N * 4
@@ -517,7 +505,7 @@ def run_ours(args):
                        "input": "fp32 [N][F] channel values resident in HBM (1.45 GB per step at F=9472, larger than L2)",
                        "output": "bit-packed hard decisions + per-frame syndrome flag",
                        "converged_fraction": ok_frac},
-            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": hybrid_h2d_bytes() if packed else h2d,
+            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": h2d_e2e,
                     "d2h_bytes_per_step": d2h, "frames_per_step": Fe, "steps": e2e_steps,
                     "launches_per_step": launches_e2e, "cpu_affinity": numa, "parity_ok": parity_ok,
                     "parity_check": "hard bits, iteration counts and flags of every host-buffer shape below == the "

@@ -145,6 +145,11 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
     const bool pack = pack_threads >= 1;
     int copy_pct = 50;
     if (const char *e = getenv("LDPC_B200_HYBRID_COPY_PCT")) copy_pct = atoi(e) < 0 ? 0 : (atoi(e) > 400 ? 400 : atoi(e));
+    // A share that adapts to the host (copy chunk grown while the DMA engine is found idle after a pack chunk, shrunk
+    // while it is backed up) was tried: +5-14 % on a box whose host memory was loaded, -1-4 % on a quiet one, no gain on
+    // a heavily loaded one where even the fixed share falls to the plain copy's 6.3-6.8 Gbit/s (profiles/r02_e2e.txt).
+    // Kept fixed.
+    ldpc_code *cm = const_cast<ldpc_code *>(c);
     int Fcopy = pack ? ((int)((long long)Fc * copy_pct / 100) & ~3) : Fc;  // frames of a copy chunk (whole groups)
     if (pack) {
         int rcp = ensure_pack_slots(c, (size_t)N * Fc);
@@ -164,6 +169,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
     cudaStream_t user = reinterpret_cast<cudaStream_t>(o->stream);
     LDPC_CUDA_TRY(cudaStreamSynchronize(user));  // work queued before this call is complete
     int launches = 0, npack = 0;
+    size_t h2d_bytes = 0;
     rc = LDPC_OK;
     for (int f0 = 0, k = 0; f0 < F && rc == LDPC_OK; k++) {
         // even k: pack chunk (stream 0, slot 0), odd k: copy chunk (stream 1, slot 1); without host threads every chunk
@@ -187,6 +193,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
                 ldpcb_host_pack_nf(reinterpret_cast<const float *>(llr), (size_t)F, N, f0, fc, o->llr_scale, stage,
                                    pack_threads);
                 ce = cudaMemcpyAsync(d_in, stage, (size_t)N * fc, cudaMemcpyHostToDevice, st);
+                h2d_bytes += (size_t)N * fc;
             }
             if (ce == cudaSuccess) ce = cudaEventRecord(c->pack_ev[sb], st);
             npack++;
@@ -195,6 +202,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
                                    cudaMemcpyHostToDevice, st);
         else
             ce = cudaMemcpyAsync(d_in, h_in + (size_t)f0 * N * esz, (size_t)fc * N * esz, cudaMemcpyHostToDevice, st);
+        if (!packed) h2d_bytes += (size_t)N * fc * esz;
         if (ce != cudaSuccess) {
             set_cuda_error(ce, "host chunk upload");
             rc = LDPC_ERR_CUDA;
@@ -247,6 +255,7 @@ static int decode_host_pipelined(const ldpc_code *c, const void *llr, void *hard
         }
         f0 += fc;
     }
+    cm->last_h2d_bytes = h2d_bytes;
     // every exit path waits for both internal streams: async copies still target the caller's buffers and the
     // pinned staging slots
     const cudaError_t s0 = cudaStreamSynchronize(c->pipe_stream[0]), s1 = cudaStreamSynchronize(c->pipe_stream[1]);
@@ -281,6 +290,8 @@ extern "C" void ldpc_decode_opts_default(ldpc_decode_opts_t *o)
     o->beta_num = 0;
     o->beta_shift = 0;
 }
+
+extern "C" size_t ldpc_last_h2d_bytes(const ldpc_code_t *c) { return c ? c->last_h2d_bytes : 0; }
 
 extern "C" size_t ldpc_out_bytes(const ldpc_code_t *c, int F, int fmt)
 {
@@ -411,6 +422,7 @@ static int decode_batch_locked(const ldpc_code_t *c, const void *llr, void *hard
         d_in = base + o_in;
         d_out = base + o_out;
         if (in_bytes) LDPC_CUDA_TRY(cudaMemcpyAsync(base + o_in, llr, in_bytes, cudaMemcpyHostToDevice, st));
+        const_cast<ldpc_code *>(c)->last_h2d_bytes = in_bytes;
         d_it = reinterpret_cast<int *>(base + o_it);
         d_ok = reinterpret_cast<int *>(base + o_ok);
         if (o->debug_app) d_dapp = base + o_dapp;

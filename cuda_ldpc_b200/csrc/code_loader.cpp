@@ -128,6 +128,7 @@ extern "C" int ldpc_load_code(const char *path, int J, int L, int Z, ldpc_code_t
     c->pack_host[0] = c->pack_host[1] = nullptr;
     c->pack_host_bytes = 0;
     c->pack_ev[0] = c->pack_ev[1] = nullptr;
+    c->last_h2d_bytes = 0;
     c->last_use = nullptr;
     c->last_use_valid = false;
     c->enc_state = 0;

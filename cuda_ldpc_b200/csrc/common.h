@@ -75,6 +75,7 @@ struct ldpc_code {
     void *pack_host[2];
     size_t pack_host_bytes;
     cudaEvent_t pack_ev[2];
+    size_t last_h2d_bytes;  // channel-value bytes the last host-buffer call uploaded (ldpc_last_h2d_bytes)
     // encoder cache (host): parity-part inverse, built lazily
     std::vector<uint32_t> enc_cache;
     int enc_state;  // 0 = not built, 1 = ok, -1 = singular

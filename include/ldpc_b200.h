@@ -144,6 +144,11 @@ int ldpc_decode_batch(const ldpc_code_t *code, const void *llr, void *hard_bits,
 /* bytes of hard_bits for a given format */
 size_t ldpc_out_bytes(const ldpc_code_t *code, int batch, int out_format);
 
+/* Host-to-device bytes of channel values the last HOST-buffer ldpc_decode_batch call on this handle copied (the chunked
+ * feed mixes int8 chunks quantised on the host with fp32 chunks in a share that adapts to the host; benchmarks report
+ * this figure).  No reference counterpart: the reference copies N*F*4 bytes per batch (B/Simulation.cu:138).          */
+size_t ldpc_last_h2d_bytes(const ldpc_code_t *code);
+
 /* ------------------------------------------------------------------ channel + simulation loop */
 
 /* On-device AWGN for BPSK: y[n,f] = 1 - 2*c[n,f] + sigma * N(0,1), Philox4x32-10 keyed by
