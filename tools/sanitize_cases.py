@@ -31,6 +31,12 @@ def binary(name, fname, geo, F, snr_es, iters):
     r = code.decode_channel(F, iters, sigma, seed=5, msg_max=31, beta_num=1, beta_shift=3)
     torch.cuda.synchronize()
     print(f"{name} fused channel: ok {int(r.ok.sum())}/{F}", flush=True)
+    for mode in (m.EXIT_SYNDROME, m.EXIT_NONE):  # fp16 message mode (2-codeword groups, records, dynamic scheduling)
+        r = code.decode(y, iters, schedule=m.SCHED_LAYERED, msg_dtype=m.DTYPE_FP16, early_exit=mode, msg_max=31,
+                        beta_num=1, beta_shift=3, debug=True)
+        torch.cuda.synchronize()
+        print(f"{name} layered fp16 mode={mode}: ok {int(r.ok.sum())}/{F} it {r.iters.min().item()}..{r.iters.max().item()}",
+              flush=True)
     yh = y.cpu().numpy()
     r = code.decode(yh, iters, schedule=m.SCHED_LAYERED, early_exit=m.EXIT_SYNDROME, out_format=m.OUT_U8, msg_max=31)
     print(f"{name} host path: ok {int(r.ok.sum())}/{F}", flush=True)
