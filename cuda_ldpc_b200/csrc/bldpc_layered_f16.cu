@@ -127,7 +127,8 @@ __device__ __forceinline__ unsigned rec_message_rt(const unsigned *w, int k)
 #ifndef LDPC_F16_MAD_ADDR
 #define LDPC_F16_MAD_ADDR 1
 #endif
-// 1: a row's record is requested one row ahead (process_row); 0: at the row's first instruction
+// 1: a row's record is requested one row ahead (process_row); 0: at the row's first instruction.  Measured: -1.5 to
+// -4 % (the five extra live registers cost more than the wait, which other warps cover)
 #ifndef LDPC_F16_PRELOAD
 #define LDPC_F16_PRELOAD 0
 #endif
@@ -361,8 +362,19 @@ __device__ void dump_messages(const F16Params &p, const uint4 *rec, int g, unsig
     }
 }
 
+// CTA width cap = register cap of the kernel (640 threads -> 96 registers, 512 -> 128, 384 -> 168) of the buckets above
+// 16, whose per-row arrays (t[] and addr[], 2 * DC registers) want more than 96.  Measured (profiles/r02_fp16_mode.txt):
+// 128 registers PON +0.7 %, J10_L60_Z160 -9 % (fewer resident CTAs); 168 registers PON -12 %: 640 stays.
+#ifndef LDPC_F16_CAP_HI
+#define LDPC_F16_CAP_HI 640
+#endif
 template <int DCMAX>
-__global__ void __launch_bounds__(640, 1) ldpc_layered_f16_kernel(const __grid_constant__ F16Params p)
+struct F16ThreadCap {
+    static constexpr int value = DCMAX > 16 ? LDPC_F16_CAP_HI : 640;
+};
+
+template <int DCMAX>
+__global__ void __launch_bounds__(F16ThreadCap<DCMAX>::value, 1) ldpc_layered_f16_kernel(const __grid_constant__ F16Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned *appw = reinterpret_cast<unsigned *>(smem);
@@ -527,7 +539,12 @@ int plan_f16(const ldpc_code *c, int F, F16Plan *pl)
 #undef X
         default: return LDPC_ERR_UNSUPPORTED;
     }
-    const int cap = 640;
+    int cap = 640;
+    switch (pl->dcb) {
+#define X(D) case D: cap = F16ThreadCap<D>::value; break;
+        LDPC_F16_BUCKETS(X)
+#undef X
+    }
     const int rows_per_thread = (c->Z + cap - 1) / cap;
     const int threads = (c->Z + rows_per_thread - 1) / rows_per_thread;
     pl->threads = (threads + 31) & ~31;
