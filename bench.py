@@ -215,6 +215,24 @@ def ncu_traffic_per_frame():
         return None, None
 
 
+def ncu_issue_pipes():
+    """an on-chip-resident design is bound by the SM issue pipes, not HBM; the pipe utilisation of the
+    dominant kernel comes from the same tracked ncu capture as roofline.traffic (not measured live: ncu is a profiler)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_layered_i8.json")) as f:
+            d = json.load(f)["C2"]
+        edges_iters = E * 10  # edge updates of one codeword in 10 iterations; a thread serves one check row of 4 codewords
+        return {"source": "profiles/r02_ncu_layered_i8.json (ncu --set full, C2, %d frames)" % d["frames"],
+                "alu_pipe_pct": d["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"],
+                "fma_pipe_pct": d["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"],
+                "fp16_pipe_pct": d["sm__inst_executed_pipe_fma_type_fp16.avg.pct_of_peak_sustained_active"],
+                "lsu_pipe_pct": d["sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"],
+                "issue_slots_busy": d["smsp__issue_active.avg.per_cycle_active"],
+                "thread_inst_per_edge_per_4_codewords": 32 * d["smsp__inst_executed.sum"] / (edges_iters * d["frames"] / 4)}
+    except Exception:
+        return None
+
+
 def timed_launches(fn, steps, torch):
     """CUDA events on the launching stream around every step; returns (total ms, mean ms per step)"""
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
@@ -539,6 +557,7 @@ def run_ours(args):
                                                     "(mostly c2v message blocks spilling from L2)",
                          "peak_source": f"{which} (MEASURED_PEAKS.json, burst copy)",
                          "kernel": "ldpc_layered_i8_kernel<8>", "kernel_ms": kern_ms,
+                         "issue_pipes": ncu_issue_pipes(),
                          "bytes_model": f"SURVEY 8(d): B_cw(10)={B_CW} B x {F} frames per launch (algorithmic bytes of a "
                                         "streaming layered decoder).  This design keeps the APP state in shared "
                                         "memory, so its real DRAM traffic is lower (traffic) and the pipes that bind are "
