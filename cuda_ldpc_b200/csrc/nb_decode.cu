@@ -46,6 +46,7 @@ struct NbParams {
     const uint16_t *mul, *inv;
     const int *vw, *cw, *v_cn, *v_pos, *c_vn, *c_gf, *c_pos;
     const float *cre, *cim;
+    int *work_counter;     // dynamic frame scheduling: frames past the first gridDim.x are handed out by an atomic counter
 };
 
 // GF(q) multiply table.  Default: the read-only path (LDG.CONSTANT; 8 KB for GF(64), 128 KB for GF(256) stay
@@ -1117,7 +1118,11 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
     const size_t ntop = p.algo == NB_ALGO_EMS ? (size_t)N * p.dv_max * kNmMax : 0;
     uint16_t *topsym = reinterpret_cast<uint16_t *>(topval + ntop);
     uint16_t *sym = topsym + ((ntop + 1) & ~(size_t)1);
-    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+    // Frame scheduling: with the syndrome stop a frame costs 1 .. maxit iterations, so a static stride leaves most CTAs
+    // idle while the unluckiest one finishes its share; CTAs draw their next frame from a counter instead (results
+    // do not depend on which CTA decodes a frame: the slot is re-initialised by demodulate()).
+    __shared__ int s_next;
+    for (int f = blockIdx.x; f < p.F;) {
         demodulate(p, f, lch, LLR);
         cta_sync();
         if (p.algo == NB_ALGO_EMS)
@@ -1128,7 +1133,9 @@ nb_decode_kernel(const __grid_constant__ NbParams p)
             decode_tmm(p, f, lch, LLR, c2v, sym, smem, &s_fail, p.algo == NB_ALGO_LAYERED_TMM);
         cta_sync();
         for (int col = threadIdx.x; col < N; col += blockDim.x) p.out[(size_t)f * N + col] = sym[col];
+        if (threadIdx.x == 0) s_next = (int)gridDim.x + atomicAdd(p.work_counter, 1);
         cta_sync();
+        f = s_next;
     }
 }
 
@@ -1289,6 +1296,8 @@ static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint
     need += ((size_t)F * 4 + a256) & ~a256;
     const size_t o_ok = need;
     need += ((size_t)F * 4 + a256) & ~a256;
+    const size_t o_ctr = need;
+    need += 256;
     {
         std::lock_guard<std::mutex> lk(g_nb_mu);
         if (c->scratch_bytes < need) {
@@ -1347,6 +1356,8 @@ static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint
     p.c_pos = c->d_c_pos;
     p.cre = c->d_cre;
     p.cim = c->d_cim;
+    p.work_counter = reinterpret_cast<int *>(base + o_ctr);
+    LDPC_CUDA_TRY(cudaMemsetAsync(p.work_counter, 0, sizeof(int), st));
     nb_decode_kernel<<<grid, threads, smem, st>>>(p);
     LDPC_CUDA_TRY(cudaGetLastError());
     if (host) {
