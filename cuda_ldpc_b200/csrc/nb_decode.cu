@@ -1261,8 +1261,11 @@ static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint
     // barrier-separated stages, is fastest as one wide CTA with the whole frame state in shared memory.
     int threads = kNbThreads, slot_in_smem = 0;
     if (o->algo == NB_ALGO_LAYERED_TMM) threads = (q + 31) & ~31;  // one q-thread group, whole warps
+    int t_first = kNbThreadsMax;
+    if (const char *e = getenv("LDPC_B200_NB_THREADS"))
+        if (atoi(e) >= kNbThreads && atoi(e) <= kNbThreadsMax && (atoi(e) & (atoi(e) - 1)) == 0) t_first = atoi(e);
     if (o->algo == NB_ALGO_FFT_BP)
-        for (int T = kNbThreadsMax; T >= kNbThreads; T >>= 1)
+        for (int T = t_first; T >= kNbThreads; T >>= 1)
             if ((work_floats_of(T) + slot_floats) * sizeof(float) <= kNbDynSmemMax) {
                 threads = T;
                 slot_in_smem = 1;
@@ -1275,6 +1278,12 @@ static int nb_decode_batch_locked(const nb_ldpc_code_t *cc, const void *in, uint
         if (o->algo == NB_ALGO_TMM && 2 * q > kNbThreads) threads = 2 * q > kNbThreadsMax ? kNbThreadsMax : 2 * q;
         if (o->algo == NB_ALGO_EMS) threads = 512;
         if ((work_floats_of(threads)) * sizeof(float) > kNbDynSmemMax) threads = kNbThreads;
+        if (const char *e = getenv("LDPC_B200_NB_THREADS")) {  // tuning knob (tools/nb_bench.py sweeps)
+            const int T = atoi(e), unit = q > 32 ? q : 32;
+            if (o->algo != NB_ALGO_LAYERED_TMM && T >= unit && T <= kNbThreadsMax && T % unit == 0 &&
+                work_floats_of(T) * sizeof(float) <= kNbDynSmemMax)
+                threads = T;
+        }
     }
     const size_t work_floats = work_floats_of(threads);
     const size_t smem = (work_floats + (slot_in_smem ? slot_floats : 0)) * sizeof(float);
