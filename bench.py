@@ -252,7 +252,8 @@ def other_configs(m, torch, dev, peak, kw):
     for name in ("C1", "C3"):
         cfg = CONFIGS[name]
         code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])
-        F = cfg["F"]
+        wave = code.wave_frames()  # whole waves of resident CTAs (ldpc_wave_frames): every CTA gets the same number of groups
+        F = max(1, round(cfg["F"] / wave)) * wave
         sigma = m.sigma_from_snr(cfg["snr"][0], cfg["snr"][1], code.rate)
         y = (1.0 + sigma * torch.randn(code.N, F, device=dev)).contiguous()
         out = torch.empty(code.out_bytes(F, m.OUT_BITPACK), dtype=torch.uint8, device=dev)
@@ -264,7 +265,7 @@ def other_configs(m, torch, dev, peak, kw):
         torch.cuda.synchronize()
         _, ms, _ = timed_launches(step, 10, torch)
         ach = F * b_cw_int8(cfg, ITERS) / (ms * 1e-3) / 1e9
-        res.append({"config": name, "mode": "layered int8, 10 iterations fixed", "frames_per_launch": F,
+        res.append({"config": name, "mode": "layered int8, 10 iterations fixed", "frames_per_launch": F, "frames_per_wave": wave,
                     "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms,
                     "roofline_frac": ach / peak, "b_cw_bytes": b_cw_int8(cfg, ITERS)})
         if name == "C3":  # BASELINE.json configs[2]: throughput mode = syndrome early termination, max 50 iterations
@@ -281,7 +282,8 @@ def other_configs(m, torch, dev, peak, kw):
     for name in ("C2", "C1", "C3"):  # fp16 message mode (★g2): same workload, half2 state, 2 codewords per CTA
         cfg = CONFIGS[name]
         code = m.LdpcCode(os.path.join(m.DATA_DIR, "bldpc", cfg["file"]), *cfg["geo"])
-        F = cfg["F"] // 2
+        wave = code.wave_frames(m.DTYPE_FP16)
+        F = max(1, round(cfg["F"] / 2 / wave)) * wave
         sigma = m.sigma_from_snr(cfg["snr"][0], cfg["snr"][1], code.rate)
         y = (1.0 + sigma * torch.randn(code.N, F, device=dev)).contiguous()
         out = torch.empty(code.out_bytes(F, m.OUT_BITPACK), dtype=torch.uint8, device=dev)
@@ -293,7 +295,7 @@ def other_configs(m, torch, dev, peak, kw):
         torch.cuda.synchronize()
         _, ms, _ = timed_launches(step, 10, torch)
         ach = F * b_cw_fp16(cfg, ITERS) / (ms * 1e-3) / 1e9
-        res.append({"config": name, "mode": "layered fp16 messages, 10 iterations fixed", "frames_per_launch": F,
+        res.append({"config": name, "mode": "layered fp16 messages, 10 iterations fixed", "frames_per_launch": F, "frames_per_wave": wave,
                     "value": F * code.K / (ms * 1e-3) / 1e9, "unit": "Gbit/s", "kernel_ms": ms,
                     "roofline_frac": ach / peak, "b_cw_bytes": b_cw_fp16(cfg, ITERS),
                     "note": "above 1: SURVEY 8d's fp16 model streams the APP values through HBM; they live in shared memory here"})

@@ -67,6 +67,8 @@ def _load():
     L.ldpc_decode_opts_default.argtypes = [C.POINTER(DecodeOpts)]
     L.ldpc_decode_opts_default.restype = None
     L.ldpc_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(DecodeOpts)]
+    L.ldpc_wave_frames.restype = C.c_int
+    L.ldpc_wave_frames.argtypes = [C.c_void_p, C.c_int]
     L.ldpc_last_h2d_bytes.restype = C.c_size_t
     L.ldpc_last_h2d_bytes.argtypes = [C.c_void_p]
     L.ldpc_out_bytes.restype = C.c_size_t

@@ -78,6 +78,14 @@ class LdpcCode:
     def out_bytes(self, F, out_format):
         return int(lib.ldpc_out_bytes(self._h, int(F), int(out_format)))
 
+    def wave_frames(self, msg_dtype=None):
+        """frames one full wave of the layered kernel's resident CTAs decodes (ldpc_wave_frames): batches that are a
+        multiple of it leave no CTA idle in the last round of a fixed-iteration decode"""
+        n = int(lib.ldpc_wave_frames(self._h, int(DTYPE_INT8 if msg_dtype is None else msg_dtype)))
+        if n < 0:
+            raise LdpcError(n, "ldpc_wave_frames")
+        return n
+
     def make_opts(self, F, **kw):
         o = DecodeOpts()
         lib.ldpc_decode_opts_default(C.byref(o))

@@ -326,6 +326,22 @@ struct DeviceGuard {
     }
 };
 
+extern "C" int ldpc_wave_frames(const ldpc_code_t *cc, int msg_dtype)
+{
+    if (!cc) return LDPC_ERR_ARG;
+    if (msg_dtype != LDPC_DTYPE_INT8 && msg_dtype != LDPC_DTYPE_FP16) return LDPC_ERR_UNSUPPORTED;
+    ldpc_code *c = const_cast<ldpc_code *>(cc);
+    std::lock_guard<std::mutex> lk(c->call_mu);
+    int rc = ensure_device(c);
+    if (rc != LDPC_OK) return rc;
+    DeviceGuard dg;
+    rc = dg.enter(c->device);
+    if (rc != LDPC_OK) return rc;
+    int frames = 0;
+    rc = msg_dtype == LDPC_DTYPE_FP16 ? layered_f16_wave_frames(c, &frames) : layered_i8_wave_frames(c, &frames);
+    return rc != LDPC_OK ? rc : frames;
+}
+
 extern "C" int ldpc_decode_batch(const ldpc_code_t *cc, const void *llr, void *hard_bits, int iters,
                                  const ldpc_decode_opts_t *o)
 {

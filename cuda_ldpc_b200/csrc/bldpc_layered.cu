@@ -825,6 +825,15 @@ static int plan_i8(const ldpc_code *c, int F, I8Plan *pl)
     return LDPC_OK;
 }
 
+int layered_i8_wave_frames(const ldpc_code *c, int *frames)
+{
+    I8Plan pl;
+    int rc = plan_i8(c, 1 << 30, &pl);
+    if (rc != LDPC_OK) return rc;
+    *frames = pl.grid * 4;  // resident CTAs x the 4 codewords of a group
+    return LDPC_OK;
+}
+
 int layered_i8_scratch_bytes(const ldpc_code *c, int F, int, size_t *bytes)
 {
     I8Plan pl;

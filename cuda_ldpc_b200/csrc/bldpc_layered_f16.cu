@@ -563,6 +563,15 @@ int plan_f16(const ldpc_code *c, int F, F16Plan *pl)
 
 }  // namespace
 
+int layered_f16_wave_frames(const ldpc_code *c, int *frames)
+{
+    F16Plan pl;
+    int rc = plan_f16(c, 1 << 30, &pl);
+    if (rc != LDPC_OK) return rc;
+    *frames = pl.grid * 2;  // resident CTAs x the 2 codewords of a group
+    return LDPC_OK;
+}
+
 int layered_f16_scratch_bytes(const ldpc_code *c, int F, size_t *bytes)
 {
     F16Plan pl;

@@ -107,6 +107,9 @@ struct LayeredArgs {
     unsigned long long ch_seed, ch_first;
     const unsigned char *ch_cw;
 };
+// frames one full wave of resident CTAs decodes (grid x codewords per group)
+int layered_i8_wave_frames(const ldpc_code *code, int *frames);
+int layered_f16_wave_frames(const ldpc_code *code, int *frames);
 // bytes of record scratch the layered kernels want for a batch of F frames
 int layered_i8_scratch_bytes(const ldpc_code *code, int F, int beta_num, size_t *bytes);
 int launch_layered_i8(const ldpc_code *code, const LayeredArgs &a, cudaStream_t st, int *launches);

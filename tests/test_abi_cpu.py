@@ -77,6 +77,16 @@ def test_decode_without_gpu_fails_loudly():
     assert e.value.code == -7
 
 
+def test_wave_frames_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    c = m.LdpcCode(os.path.join(BL, "J4_L24_Z96_BlockH.txt"))
+    assert m.lib.ldpc_wave_frames(c.handle, m.DTYPE_INT8) == -7
+    assert m.lib.ldpc_wave_frames(c.handle, m.DTYPE_FP32) == -6  # only the layered int8 / fp16 kernels have waves
+    assert m.lib.ldpc_wave_frames(None, m.DTYPE_INT8) == -3
+
+
 def test_no_product_code_touches_the_oracle():
     """The product path must never import, link or execute anything under oracle/."""
     bad = []

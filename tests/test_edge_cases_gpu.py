@@ -78,3 +78,21 @@ def test_error_contract_returns_codes_and_decodes_nothing(oracle):
     assert (out == 0x5A).all(), "a rejected call must not touch the output buffer"
     assert m.lib.ldpc_strerror(ERR_UNSUP).decode() and m.lib.ldpc_strerror(-12345).decode()
     assert call() >= 1  # and the handle still works afterwards
+
+
+def test_wave_frames_batches_decode_bit_exact(oracle):
+    """ldpc_wave_frames = resident CTAs x codewords per group; batches of one wave and one wave + 1 frame decode
+    bit for bit like the oracle (checked on the first and last 8 frames)"""
+    import torch
+    code, oc = load(oracle, "C1")
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    w8, w16 = code.wave_frames(), code.wave_frames(m.DTYPE_FP16)
+    assert w8 > 0 and w8 % (4 * sms) == 0
+    assert w16 > 0 and w16 % (2 * sms) == 0
+    assert m.lib.ldpc_wave_frames(code.handle, m.DTYPE_FP32) == -6
+    for F in (w8, w8 + 1):
+        y = noisy(oracle, code.N, F, 2.8)
+        r = code.decode(y, 5, schedule=m.SCHED_LAYERED, msg_max=31, beta_num=1, beta_shift=3)
+        sl = np.r_[0:8, F - 8:F]
+        D, its, _, _ = orc_i8(oracle, oc, np.ascontiguousarray(y[:, sl]), 5, m.EXIT_NONE, amax=31, bnum=1, bshift=3)
+        assert (r.D[:, sl] == D).all() and (r.iters[sl] == its).all()
