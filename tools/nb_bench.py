@@ -16,7 +16,9 @@ CASES = [("C4 GF64 64QAM EMS(2,2)", "LDPC_N576_K288_GF64_d1_exp.txt", "GRAY_64QA
          ("C5 GF256 BPSK TMM", "LDPC_N576_K480_GF256_exp.txt", "BPSK.txt", 2, 4.5, m.ALGO_TMM, 4096),
          ("C5 GF256 BPSK layered TMM", "LDPC_N576_K480_GF256_exp.txt", "BPSK.txt", 2, 4.5, m.ALGO_LAYERED_TMM, 4096)]
 print(torch.cuda.get_device_name(0))
+FSCALE = int(os.environ.get("NB_BENCH_FSCALE", "1"))  # SURVEY 8(d) asks for F >= 16384: NB_BENCH_FSCALE=2 / 4
 for name, mat, cst, nqam, ebn0, algo, F in CASES:
+    F *= FSCALE
     code = m.NbLdpcCode(os.path.join(NB, mat), None, os.path.join(NB, "Constellation", cst), coef_is_exponent=mat.endswith("_exp.txt"))
     rate = (code.N - code.M) / code.N
     sigma = float(np.sqrt(0.5 / (np.log2(nqam) * rate * 10 ** (ebn0 / 10))))
